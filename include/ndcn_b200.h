@@ -1,0 +1,162 @@
+/*
+ * ndcn_b200.h -- C ABI of libndcn_b200.so (hand-written sm_100a CUDA kernels for the
+ * NDCN ODE-integrated graph-convolution hot path).
+ *
+ * The reference (calvin-zcx/ndcn) is pure Python and has NO native/FFI boundary; its hot
+ * path is reached through the Python operator surface (neural_dynamics.ODEFunc / ODEBlock /
+ * NDCN, torchdiffeq.odeint).  This header is the boundary a maintainer would bind instead
+ * (ctypes stub in INTEGRATION.md): each entry point names the reference call site it
+ * replaces (file:line into the upstream tree).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument (NDCN_E_*), >0 a cudaError_t;
+ *   - no exceptions, no torch types, plain pointers and sizes;
+ *   - all data pointers are BORROWED DEVICE pointers unless the name ends in _host;
+ *     the caller (PyTorch) owns every buffer, including the solver workspace;
+ *   - every launch goes to the explicit stream argument (a cudaStream_t);
+ *   - fp32 state, int32 CSR indices, float64 solver times;
+ *   - handles are thread-compatible: one handle, one stream at a time.
+ */
+#ifndef NDCN_B200_H
+#define NDCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ndcn_stream_t;            /* cudaStream_t */
+typedef struct ndcn_graph ndcn_graph_t; /* CSR operator Phi on the device */
+typedef struct ndcn_solver ndcn_solver_t;
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define NDCN_OK 0
+#define NDCN_E_ARG (-1)        /* null pointer / bad size / unsupported combination */
+#define NDCN_E_WORKSPACE (-2)  /* workspace too small */
+#define NDCN_E_METHOD (-3)     /* method not in {euler, midpoint, rk4, dopri5} */
+#define NDCN_E_NONFINITE (-10) /* "non-finite values in state `y`"  (dopri5.py:102)   */
+#define NDCN_E_DT_UNDERFLOW (-11) /* "underflow in dt"              (dopri5.py:100)   */
+#define NDCN_E_MAX_STEPS (-12) /* "max_num_steps exceeded"          (dopri5.py:89)    */
+
+/* ---- right-hand sides -------------------------------------------------------------- */
+enum ndcn_rhs_kind {
+  NDCN_RHS_NDCN = 0,   /* relu((Phi x) W^T + b)      neural_dynamics.py:20-39            */
+  NDCN_RHS_HEAT = 1,   /* k * (Phi x), Phi = -L      heat_dynamics.py:186-204            */
+  NDCN_RHS_GENE = 2,   /* -b x^f + Phi(x^h/(x^h+1))  gene_dynamics.py:186-205            */
+  NDCN_RHS_MUTUAL = 3, /* b + x(1-x/k)(x/c-1) + sum_j a_ij x_i x_j/(d + ...)
+                          mutualistic_dynamics.py:186-232 (both branches, chosen by H==1) */
+  NDCN_RHS_CALLBACK = 4 /* any callable func(t, y): the solver algebra stays fused, the
+                          RHS is produced by the host callback   (odeint.py:20 `func`)    */
+};
+
+/* flags for NDCN_RHS_NDCN (ODEFunc ctor switches, neural_dynamics.py:9-18) */
+#define NDCN_F_NO_GRAPH 1u   /* skip Phi          */
+#define NDCN_F_NO_CONTROL 2u /* skip Linear(W,b)  */
+#define NDCN_F_NO_RELU 4u    /* (stand-alone SpMM / Linear only; never set by ODEFunc) */
+
+typedef int (*ndcn_rhs_callback_t)(void* user, const float* y_dev, float* k_dev,
+                                   const float* t_dev /* fp32 stage time on the device */);
+/* multi-GPU hook, called on the launching thread between kernels:
+ *   what = 0: `buf` ([n_cols, H], first n_rows rows valid) needs its halo rows
+ *             (rows n_rows..n_cols-1) filled from the owning ranks;
+ *   what = 1: `buf` points at 2 doubles {sum of squared error ratios, element count}
+ *             to be all-reduced (SUM) in place.                                         */
+typedef int (*ndcn_exchange_callback_t)(void* user, int what, void* buf_dev);
+
+typedef struct ndcn_rhs_desc {
+  int32_t kind;  /* enum ndcn_rhs_kind */
+  uint32_t flags;
+  int32_t H;     /* state width (columns of x) */
+  int32_t reserved;
+  const float* W; /* [H,H] row-major, y = x W^T + b (nn.Linear)  -- NDCN only */
+  const float* b; /* [H]                                          -- NDCN only */
+  /* HEAT: p[0]=k.  GENE: p[0]=b, p[1]=f, p[2]=h.  MUTUAL: p[0..5] = b,k,c,d,e,h */
+  float p[8];
+  ndcn_rhs_callback_t callback; /* CALLBACK only */
+  void* callback_user;
+} ndcn_rhs_desc_t;
+
+/* ---- graph handle ------------------------------------------------------------------
+ * Replaces the operator tensor captured by ODEFunc.A / HeatDiffusion.L / *.A
+ * (neural_dynamics.py:14, heat_dynamics.py:190): dense or uncoalesced-COO there, int32 CSR
+ * here (built once by the host layer).  n_cols >= n_rows: rows [n_rows, n_cols) of every
+ * gather source are halo rows owned by other ranks (n_cols == n_rows on one GPU).        */
+int ndcn_graph_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+                      const int32_t* col, const float* val, ndcn_graph_t** out);
+int ndcn_graph_destroy(ndcn_graph_t* g);
+
+/* ---- stand-alone operators (one RHS evaluation) --------------------------------------- */
+/* y = Phi x           torch.sparse.mm / torch.mm at neural_dynamics.py:27-31            */
+int ndcn_spmm_f32(const ndcn_graph_t* g, const float* x, float* y, int32_t H, ndcn_stream_t s);
+/* out = f(x) for any rhs kind except CALLBACK: ODEFunc.forward neural_dynamics.py:20-39,
+ * HeatDiffusion/GeneDynamics/MutualDynamics.forward (files above)                        */
+int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x,
+                      float* out, ndcn_stream_t s);
+
+/* ---- solver -------------------------------------------------------------------------- */
+enum ndcn_method { NDCN_EULER = 0, NDCN_MIDPOINT = 1, NDCN_RK4 = 2, NDCN_DOPRI5 = 3 };
+
+#define NDCN_O_TERMINAL_ONLY 1u /* out holds only y(t[-1])  (ODEBlock terminal=True)      */
+#define NDCN_O_FORCED_DT 2u     /* dopri5: every step accepted, dt = forced_dt            */
+
+typedef struct ndcn_solve_opts {
+  int32_t method;   /* enum ndcn_method */
+  uint32_t flags;
+  double rtol, atol;           /* dopri5 only (fixed-grid solvers ignore them, solvers.py:40-41) */
+  double forced_dt;            /* with NDCN_O_FORCED_DT */
+  int64_t max_num_steps;       /* per output interval, dopri5.py:89; <=0: 2^31-1 */
+  ndcn_exchange_callback_t exchange; /* NULL on one GPU */
+  void* exchange_user;
+  double safety, ifactor, dfactor; /* 0 => dopri5.py:60 defaults .9 / 10 / .2 */
+} ndcn_solve_opts_t;
+
+typedef struct ndcn_solve_stats {
+  int64_t nfe;        /* RHS evaluations                   */
+  int64_t n_accepted; /* accepted steps (all, fixed grid)  */
+  int64_t n_rejected;
+  int64_t n_launches; /* kernels launched by this solve    */
+  double first_step;  /* dopri5 initial dt (misc.py:84)    */
+  double last_dt;
+  double t_final;     /* end of last accepted step         */
+  int32_t status;     /* NDCN_OK or an NDCN_E_* solver error */
+  int32_t reserved;
+} ndcn_solve_stats_t;
+
+/* bytes of device workspace ndcn_solver_create needs for this problem */
+size_t ndcn_solver_workspace_bytes(int64_t n_rows, int64_t n_cols, int32_t H, int32_t method);
+
+int ndcn_solver_create(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, int32_t method,
+                       void* workspace_dev, size_t workspace_bytes, ndcn_solver_t** out);
+int ndcn_solver_destroy(ndcn_solver_t* sv);
+
+/* torchdiffeq.odeint(func, y0, t, rtol, atol, method)    torchdiffeq/_impl/odeint.py:20-76
+ *   y0     [n_rows, H] fp32 device
+ *   t_host [n_t] float64 HOST, strictly increasing; the caller has already applied the
+ *          reference's dtype round trips (ODEBlock rounds vt to fp32 first,
+ *          neural_dynamics.py:71; the adaptive driver then promotes, solvers.py:28)
+ *   out    [n_t, n_rows, H] (or [n_rows, H] with NDCN_O_TERMINAL_ONLY); out[0] = y0
+ * Enqueues on `s`; synchronises `s` before returning (stats are final on return).      */
+int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t,
+                    float* out, const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats,
+                    ndcn_stream_t s);
+
+/* ---- solver algebra as stand-alone kernels (used by tests and by generic callers) ----- */
+/* out = y0 + sum_j (dt*beta_j) k_j, reference rounding (misc.py:22-25, rk_common.py:50) */
+int ndcn_rk_combine_f32(float* out, const float* y0, const float* const* k_host_ptrs,
+                        const double* beta_host, int32_t n_k, float dt, int64_t numel,
+                        ndcn_stream_t s);
+/* sum over elements of (err/(atol+rtol*max(|y0|,|y1|)))^2 -> *sum_out (double, device)
+ * misc.py:146-157                                                                       */
+int ndcn_error_ratio_f32(const float* err, const float* y0, const float* y1, double rtol,
+                         double atol, int64_t numel, double* sum_out_dev, ndcn_stream_t s);
+
+/* library / build information */
+const char* ndcn_version(void);
+int ndcn_sm_arch(void); /* 100: built for sm_100a */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDCN_B200_H */

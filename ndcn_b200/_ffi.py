@@ -1,0 +1,130 @@
+"""ctypes binding of libndcn_b200.so (the C ABI declared in include/ndcn_b200.h).
+
+There is NO fallback: if the library is missing or does not export a declared symbol,
+loading raises.  Every compute entry point of the package goes through ``lib()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from . import _build
+
+c_float_p = C.POINTER(C.c_float)
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+RHS_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+EXCHANGE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+
+# status codes (include/ndcn_b200.h)
+OK = 0
+E_ARG, E_WORKSPACE, E_METHOD = -1, -2, -3
+E_NONFINITE, E_DT_UNDERFLOW, E_MAX_STEPS = -10, -11, -12
+
+RHS_NDCN, RHS_HEAT, RHS_GENE, RHS_MUTUAL, RHS_CALLBACK_KIND = 0, 1, 2, 3, 4
+F_NO_GRAPH, F_NO_CONTROL, F_NO_RELU = 1, 2, 4
+EULER, MIDPOINT, RK4, DOPRI5 = 0, 1, 2, 3
+METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4, "dopri5": DOPRI5}
+O_TERMINAL_ONLY, O_FORCED_DT = 1, 2
+
+
+class RhsDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("flags", C.c_uint32), ("H", C.c_int32), ("reserved", C.c_int32),
+        ("W", C.c_void_p), ("b", C.c_void_p), ("p", C.c_float * 8),
+        ("callback", RHS_CALLBACK), ("callback_user", C.c_void_p),
+    ]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [
+        ("method", C.c_int32), ("flags", C.c_uint32), ("rtol", C.c_double), ("atol", C.c_double),
+        ("forced_dt", C.c_double), ("max_num_steps", C.c_int64),
+        ("exchange", EXCHANGE_CALLBACK), ("exchange_user", C.c_void_p),
+        ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double),
+    ]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [
+        ("nfe", C.c_int64), ("n_accepted", C.c_int64), ("n_rejected", C.c_int64), ("n_launches", C.c_int64),
+        ("first_step", C.c_double), ("last_dt", C.c_double), ("t_final", C.c_double),
+        ("status", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); kept in sync with include/ndcn_b200.h (tests/test_abi.py checks)
+PROTOTYPES = {
+    "ndcn_graph_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_void_p)]),
+    "ndcn_graph_destroy": (C.c_int, [C.c_void_p]),
+    "ndcn_spmm_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "ndcn_rhs_eval_f32": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ndcn_solver_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "ndcn_solver_create": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_int32, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_void_p)]),
+    "ndcn_solver_destroy": (C.c_int, [C.c_void_p]),
+    "ndcn_odeint_f32": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int32, C.c_void_p,
+                                  C.POINTER(SolveOpts), C.POINTER(SolveStats), C.c_void_p]),
+    "ndcn_rk_combine_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), c_double_p, C.c_int32,
+                                      C.c_float, C.c_int64, C.c_void_p]),
+    "ndcn_error_ratio_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int64,
+                                       C.c_void_p, C.c_void_p]),
+    "ndcn_version": (C.c_char_p, []),
+    "ndcn_sm_arch": (C.c_int, []),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class NdcnLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises NdcnLibraryError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        raise NdcnLibraryError(
+            "libndcn_b200.so is not built (%s). Run `python -m ndcn_b200._build` or "
+            "__graft_entry__.build(); there is no CPU/PyTorch fallback for the hot path." % path)
+    try:
+        handle = C.CDLL(path)
+    except OSError as exc:  # pragma: no cover
+        raise NdcnLibraryError("cannot load %s: %s" % (path, exc)) from exc
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as exc:
+            raise NdcnLibraryError("libndcn_b200.so lacks symbol %s" % name) from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = handle
+    return handle
+
+
+_MESSAGES = {
+    E_ARG: "invalid argument",
+    E_WORKSPACE: "workspace too small",
+    E_METHOD: "unsupported method",
+    E_NONFINITE: "non-finite values in state `y`",
+    E_DT_UNDERFLOW: "underflow in dt",
+    E_MAX_STEPS: "max_num_steps exceeded",
+}
+
+
+def check(rc: int, what: str = "ndcn call") -> None:
+    """Map a status code to the exception type the reference raises for the same condition."""
+    if rc == OK:
+        return
+    if rc in (E_NONFINITE, E_DT_UNDERFLOW, E_MAX_STEPS):
+        # the reference signals these with bare ``assert`` (dopri5.py:89,100,102)
+        raise AssertionError(_MESSAGES[rc])
+    if rc < 0:
+        raise ValueError("%s: %s (status %d)" % (what, _MESSAGES.get(rc, "error"), rc))
+    raise RuntimeError("%s: CUDA error %d" % (what, rc))

@@ -1,0 +1,187 @@
+"""Differentiable / generic solve path (CUDA tensors, autograd-visible).
+
+Used when (a) gradients must flow through the solver -- every training loop of the reference
+backpropagates through ``odeint`` with plain autograd (heat_dynamics.py:333, dgnn.py:204;
+SURVEY.md section 3.5) -- or (b) ``func`` is an arbitrary callable the fused kernels do not know.
+The state stays on the GPU; the RHS of a recognised ``ODEFunc`` still runs the hand-written
+SpMM kernel through ``SpmmFn`` (forward Phi x, backward Phi^T g).  The solver algebra here is
+issued as PyTorch ops so that autograd records it, with the same operation order as
+torchdiffeq/_impl (so training trajectories track the reference's); the fully fused
+backward is the "next" row N1 of SURVEY.md section 8(f) and is NOT claimed by this module.
+
+There is no CPU execution here: inputs must be CUDA tensors.
+"""
+from __future__ import annotations
+
+from typing import Callable, List
+
+import torch
+
+from . import solver as _solver
+from .graph import CsrGraph
+
+# Dormand-Prince(5,4)/Shampine tableau (torchdiffeq/_impl/dopri5.py:11-36)
+_A = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
+_B = (
+    (1 / 5,),
+    (3 / 40, 9 / 40),
+    (44 / 45, -56 / 15, 32 / 9),
+    (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+    (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656),
+    (35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84),
+)
+_E = (35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+      -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0)
+_M = (6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+      187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2)
+
+
+class SpmmFn(torch.autograd.Function):
+    """Phi @ x on the CUDA SpMM kernel; d/dx = Phi^T @ g on the same kernel (transposed CSR)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, graph: CsrGraph) -> torch.Tensor:
+        ctx.graph = graph
+        return _solver.spmm(graph, x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        return _solver.spmm(ctx.graph.transpose(), g.contiguous()), None
+
+
+def _require_cuda_state(y0: torch.Tensor) -> None:
+    if not y0.is_cuda:
+        raise RuntimeError(
+            "ndcn_b200: the differentiable / generic solve path needs CUDA tensors (run the script with "
+            "--gpu 0 / without --no-cuda); there is no CPU fallback in this backend.")
+
+
+def _wsum(dt, coeffs, ks):
+    acc = 0
+    for c, k in zip(coeffs, ks):
+        acc = acc + (dt * c) * k  # misc.py:22-25
+    return acc
+
+
+def _rms(x):
+    return x.norm() / (x.numel() ** 0.5)
+
+
+def _first_step(func, t0, y0, order, rtol, atol, f0):  # misc.py:84-143
+    t0 = t0.to(y0)
+    scale = atol + torch.abs(y0) * rtol
+    d0, d1 = _rms(y0 / scale), _rms(f0 / scale)
+    if d0.item() < 1e-5 or d1.item() < 1e-5:
+        h0 = torch.tensor(1e-6).to(t0)
+    else:
+        h0 = 0.01 * (d0 / d1)
+    f1 = func(t0 + h0, y0 + h0 * f0)
+    d2 = _rms((f1 - f0) / scale) / h0
+    if d1.item() <= 1e-15 and d2.item() <= 1e-15:
+        h1 = torch.max(torch.tensor(1e-6).to(h0), h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / float(order + 1))
+    return torch.min(100 * h0, h1)
+
+
+def _as64(v, device):
+    return torch.tensor(v).type(torch.float64).to(device)  # misc.py:39-47: via an fp32 tensor
+
+
+def _resize(dt, msr, dev):  # misc.py:160-170 with dopri5.py:71-73's constants
+    safety, ifactor, dfactor = _as64(0.9, dev), _as64(10.0, dev), _as64(0.2, dev)
+    if msr == 0:
+        return dt * ifactor
+    if msr < 1:
+        dfactor = _as64(1, dev)
+    root = torch.sqrt(msr).to(dt)
+    expo = torch.tensor(1 / 5).to(dt)
+    return dt / torch.max(1 / ifactor, torch.min(root ** expo / safety, 1 / dfactor))
+
+
+def _dense_coeffs(y0, y1, ks, dt):  # dopri5.py:39-45, interp.py:5-35
+    ymid = y0 + _wsum(dt, _M, ks)
+    f0, f1 = ks[0], ks[-1]
+    vs = (f0, f1, y0, y1, ymid)
+
+    def dot(ws):
+        acc = 0
+        for w, v in zip(ws, vs):
+            acc = acc + w * v
+        return acc
+
+    return [dot((-2 * dt, 2 * dt, -8, -8, 16)), dot((5 * dt, -3 * dt, 18, 14, -32)),
+            dot((-4 * dt, dt, -11, -5, 16)), dt * f0, y0]
+
+
+def _dense_eval(cs, t0, t1, t):  # interp.py:38-65
+    dtype, dev = cs[0].dtype, cs[0].device
+    t0, t1, t = t0.to(dev, dtype), t1.to(dev, dtype), t.to(dev, dtype)
+    assert (t0 <= t) & (t <= t1), "invalid interpolation, fails `t0 <= t <= t1`: {}, {}, {}".format(t0, t, t1)
+    x = ((t - t0) / (t1 - t0)).type(dtype)
+    xs = [torch.tensor(1).type(dtype).to(dev), x]
+    for _ in range(2, len(cs)):
+        xs.append(xs[-1] * x)
+    acc = 0
+    for c, xp in zip(cs, reversed(xs)):
+        acc = acc + c * xp
+    return acc
+
+
+def solve(func: Callable, y0: torch.Tensor, t: torch.Tensor, rtol: float, atol: float, method: str,
+          max_num_steps: int = 2 ** 31 - 1) -> torch.Tensor:
+    """Single-tensor odeint on CUDA tensors with autograd (euler | midpoint | rk4 | dopri5)."""
+    _require_cuda_state(y0)
+    assert (t[1:] > t[:-1]).all(), "t must be strictly increasing or decrasing"
+    outs: List[torch.Tensor] = [y0]
+    if method in ("euler", "midpoint", "rk4"):  # solvers.py:79-99, fixed_grid.py, rk_common.py:72-78
+        tt = t.type_as(y0).to(y0.device)
+        y = y0
+        for t0, t1 in zip(tt[:-1], tt[1:]):
+            dt = t1 - t0
+            if method == "euler":
+                dy = dt * func(t0, y)
+            elif method == "midpoint":
+                dy = dt * func(t0 + dt / 2, y + func(t0, y) * dt / 2)
+            else:
+                k1 = func(t0, y)
+                k2 = func(t0 + dt / 3, y + dt * k1 / 3)
+                k3 = func(t0 + dt * 2 / 3, y + dt * (k1 / -3 + k2))
+                k4 = func(t0 + dt, y + dt * (k1 - k2 + k3))
+                dy = (k1 + 3 * k2 + 3 * k3 + k4) * (dt / 8)
+            y = y + dy
+            outs.append(y)
+        return torch.stack(outs)
+    if method != "dopri5":
+        raise ValueError("ndcn_b200 covers euler | midpoint | rk4 | dopri5, got %r" % (method,))
+    # solvers.py:25-33, dopri5.py:58-122
+    dev = y0.device
+    t = t.to(dev, torch.float64)
+    f = func(t[0].type_as(y0), y0)
+    dt = _first_step(func, t[0], y0, 4, rtol, atol, f).to(t)
+    y, lo, hi = y0, t[0], t[0]
+    cs = [y0] * 5
+    for i in range(1, len(t)):
+        n = 0
+        while t[i] > hi:
+            assert n < max_num_steps, "max_num_steps exceeded ({}>={})".format(n, max_num_steps)
+            assert hi + dt > hi, "underflow in dt {}".format(dt.item())
+            assert bool(torch.isfinite(y).all()), "non-finite values in state `y`: {}".format(y)
+            h = dt.type(y.dtype)
+            tb = hi.type(y.dtype)
+            ks = [f]
+            ys = y
+            for a, b in zip(_A, _B):
+                ys = y + _wsum(h, b, ks)
+                ks.append(func(tb + a * h, ys))
+            err = _wsum(h, _E, ks)
+            ratio = err / (atol + rtol * torch.max(torch.abs(y), torch.abs(ys)))
+            msr = torch.mean(ratio * ratio)
+            lo = hi
+            if bool(msr <= 1):
+                cs = _dense_coeffs(y, ys, ks, h)
+                y, f, hi = ys, ks[-1], hi + dt
+            dt = _resize(dt, msr, dev)
+            n += 1
+        outs.append(_dense_eval(cs, lo, hi, t[i]))
+    return torch.stack(outs)

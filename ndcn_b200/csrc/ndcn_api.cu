@@ -1,0 +1,753 @@
+// C ABI of libndcn_b200.so + the host-side solve drivers (see include/ndcn_b200.h).
+//
+// The drivers only ENQUEUE: the adaptive dopri5 loop keeps t, dt, accept/reject, the FSAL
+// buffer parity and the dense-output bookkeeping in a device-resident controller block and
+// polls it once per batch of step attempts (reference: >=3 host syncs per step,
+// torchdiffeq/_impl/dopri5.py:88-109).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ndcn_common.cuh"
+#include "solver_kernels.cuh"
+#include "stage_kernels.cuh"
+
+using namespace ndcn;
+
+#define CU_TRY(expr)                          \
+  do {                                        \
+    cudaError_t _e = (expr);                  \
+    if (_e != cudaSuccess) return (int)_e;    \
+  } while (0)
+#define RC_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != 0) return _rc;   \
+  } while (0)
+
+struct ndcn_graph {
+  GraphView v;
+};
+
+// Dormand-Prince / Shampine tableau, torchdiffeq/_impl/dopri5.py:11-36 (doubles, cast to fp32
+// exactly where the reference's tensor*python-float multiplication does, misc.py:25)
+static const double kDpBeta[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
+};
+static const double kDpErr[7] = {
+    35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+    -2187.0 / 6784 - -12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60.0,
+};
+static const double kDpMid[7] = {
+    6025192743.0 / 30085553152.0 / 2, 0, 51252292925.0 / 65400821598.0 / 2, -2691868925.0 / 45128329728.0 / 2,
+    187940372067.0 / 1594534317056.0 / 2, -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2,
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline PtrPair pp(float* a) { return PtrPair{{a, a}}; }
+static inline PtrPair pp(float* a, float* b) { return PtrPair{{a, b}}; }
+
+struct ndcn_solver {
+  const ndcn_graph* g = nullptr;
+  ndcn_rhs_desc_t rhs{};
+  int method = 0;
+  int64_t n_rows = 0, n_cols = 0;
+  int H = 0;
+  int64_t numel = 0;      // n_rows * H
+  int64_t numel_src = 0;  // n_cols * H
+  // caller-provided workspace
+  float* Y[2] = {nullptr, nullptr};   // state ping-pong (gather sources, n_cols rows)
+  float* YS[2] = {nullptr, nullptr};  // stage inputs (gather sources, n_cols rows)
+  float* KF[2] = {nullptr, nullptr};  // f0 / k7 (FSAL pair)
+  float* K[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* Wt = nullptr;
+  // library-owned control scratch
+  double* partials = nullptr;
+  int max_partials = 0;
+  double* xchg = nullptr;     // 2 doubles for the multi-GPU all-reduce hook
+  float* t_stage = nullptr;   // fp32 stage time for callback RHS
+  double* t_out = nullptr;
+  int t_cap = 0;
+  Ctrl* ctrl = nullptr;
+  Ctrl* ctrl_host = nullptr;  // pinned
+  int64_t launches = 0;
+  int sm_count = 148;
+};
+
+// ---------------------------------------------------------------------------------------
+// RHS stage dispatch
+// ---------------------------------------------------------------------------------------
+static int grid_for_elems(int64_t n, int sm_count) {
+  int64_t blocks = (n + kStageThreads * 4 - 1) / (kStageThreads * 4);
+  int64_t cap = (int64_t)sm_count * 16;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+template <int VW, int NCH>
+static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaStream_t st) {
+  const int64_t n = a.g.n_rows;
+  if (a.flags & NDCN_F_NO_CONTROL) {
+    const int grid = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta);
+    *grid_out = grid;
+    k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
+  } else {
+    using S = GemmSmem<VW, NCH>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_TRY(cudaFuncSetAttribute(k_stage_ndcn_gemm<VW, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)S::total));
+      attr_set = true;
+    }
+    const int grid = (int)((n + kTileRows - 1) / kTileRows);
+    *grid_out = grid;
+    k_stage_ndcn_gemm<VW, NCH><<<grid, kStageThreads, S::total, st>>>(a, e);
+  }
+  return (int)cudaGetLastError();
+}
+
+template <int KIND>
+static int launch_dyn(const DynArgs& a, EpiArgs& e, double avg_deg, int* grid_out, cudaStream_t st) {
+  const int64_t n = a.g.n_rows;
+  if (a.d == 1) {
+    int lpr = 4;
+    if (avg_deg > 24) lpr = 32;
+    else if (avg_deg > 12) lpr = 16;
+    else if (avg_deg > 6) lpr = 8;
+    const int64_t rows_per_block = (int64_t)kStageThreads / lpr;
+    const int grid = (int)((n + rows_per_block - 1) / rows_per_block);
+    *grid_out = grid;
+    switch (lpr) {
+      case 4: k_stage_dyn1<KIND, 4><<<grid, kStageThreads, 0, st>>>(a, e); break;
+      case 8: k_stage_dyn1<KIND, 8><<<grid, kStageThreads, 0, st>>>(a, e); break;
+      case 16: k_stage_dyn1<KIND, 16><<<grid, kStageThreads, 0, st>>>(a, e); break;
+      default: k_stage_dyn1<KIND, 32><<<grid, kStageThreads, 0, st>>>(a, e); break;
+    }
+  } else {
+    const int grid = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta);
+    *grid_out = grid;
+    k_stage_dynv<KIND><<<grid, kStageThreads, 0, st>>>(a, e);
+  }
+  return (int)cudaGetLastError();
+}
+
+struct RhsBinding {  // everything needed to launch one RHS stage
+  const ndcn_graph* g;
+  const ndcn_rhs_desc_t* rhs;
+  const float* Wt;
+  double* partials;
+  int max_partials;
+  int sm_count;
+};
+
+// Launches f(src) fused with epilogue `e`; returns the number of per-CTA partial slots the
+// kernel writes in EPI_ERR mode through *n_partials.
+static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_partials, cudaStream_t st) {
+  const ndcn_rhs_desc_t& r = *b.rhs;
+  e.partials = b.partials;
+  int grid = 0;
+  int rc = 0;
+  if (r.kind == NDCN_RHS_NDCN) {
+    NdcnArgs a;
+    a.g = b.g->v;
+    a.x = src;
+    a.Wt = b.Wt;
+    a.bias = r.b;
+    a.flags = r.flags;
+    const bool need_w = !(r.flags & NDCN_F_NO_CONTROL);
+    if (need_w && (r.W == nullptr || r.b == nullptr)) return NDCN_E_ARG;
+    switch (r.H) {
+      case 256: rc = launch_ndcn_fast<4, 2>(a, e, &grid, st); break;
+      case 128: rc = launch_ndcn_fast<4, 1>(a, e, &grid, st); break;
+      case 64: rc = launch_ndcn_fast<2, 1>(a, e, &grid, st); break;
+      case 32: rc = launch_ndcn_fast<1, 1>(a, e, &grid, st); break;
+      default: {
+        if (r.H < 1 || r.H > 1024) return NDCN_E_ARG;
+        grid = (int)((a.g.n_rows + kWarpsPerCta - 1) / kWarpsPerCta);
+        const size_t smem = sizeof(float) * kWarpsPerCta * r.H;
+        k_stage_ndcn_any<<<grid, kStageThreads, smem, st>>>(a, r.H, r.W, e);
+        rc = (int)cudaGetLastError();
+      }
+    }
+  } else if (r.kind == NDCN_RHS_HEAT || r.kind == NDCN_RHS_GENE || r.kind == NDCN_RHS_MUTUAL) {
+    DynArgs a;
+    a.g = b.g->v;
+    a.x = src;
+    a.kind = r.kind;
+    a.d = r.H;
+    for (int i = 0; i < 8; ++i) a.p[i] = r.p[i];
+    const double avg = a.g.n_rows > 0 ? (double)a.g.nnz / (double)a.g.n_rows : 0.0;
+    if (r.kind == NDCN_RHS_HEAT) rc = launch_dyn<NDCN_RHS_HEAT>(a, e, avg, &grid, st);
+    else if (r.kind == NDCN_RHS_GENE) rc = launch_dyn<NDCN_RHS_GENE>(a, e, avg, &grid, st);
+    else rc = launch_dyn<NDCN_RHS_MUTUAL>(a, e, avg, &grid, st);
+  } else {
+    return NDCN_E_ARG;
+  }
+  if (rc != 0) return rc;
+  if (e.mode == EPI_ERR && grid > b.max_partials) return NDCN_E_WORKSPACE;
+  if (n_partials) *n_partials = grid;
+  return 0;
+}
+
+static int max_partials_for(int64_t n_rows, int H) {
+  // upper bound over every stage kernel's grid: the [N,1] kernels with 4 lanes per row
+  int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32);  // warp per row / LPR=32
+  int64_t by_lpr4 = (n_rows + 63) / 64;
+  (void)H;
+  return (int)std::max<int64_t>(std::max(by_rows, by_lpr4), 148 * 16) + 8;
+}
+
+// ---------------------------------------------------------------------------------------
+// graph handle
+// ---------------------------------------------------------------------------------------
+extern "C" int ndcn_graph_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+                                 const int32_t* col, const float* val, ndcn_graph_t** out) {
+  if (!out || n_rows < 0 || n_cols < n_rows || nnz < 0 || !rowptr) return NDCN_E_ARG;
+  if (nnz > 0 && (!col || !val)) return NDCN_E_ARG;
+  if (nnz > 0x7fffffffLL || n_cols > 0x7fffffffLL) return NDCN_E_ARG;  // int32 CSR
+  ndcn_graph* g = new (std::nothrow) ndcn_graph();
+  if (!g) return NDCN_E_ARG;
+  g->v.rowptr = rowptr;
+  g->v.col = col;
+  g->v.val = val;
+  g->v.n_rows = n_rows;
+  g->v.n_cols = n_cols;
+  g->v.nnz = nnz;
+  *out = g;
+  return NDCN_OK;
+}
+
+extern "C" int ndcn_graph_destroy(ndcn_graph_t* g) {
+  delete g;
+  return NDCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stand-alone operators
+// ---------------------------------------------------------------------------------------
+static EpiArgs store_only(float* out) {
+  EpiArgs e;
+  std::memset(&e, 0, sizeof(e));
+  e.mode = EPI_STORE;
+  e.k_out = pp(out);
+  return e;
+}
+
+extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x, float* out,
+                                 ndcn_stream_t s) {
+  if (!g || !rhs || !x || !out) return NDCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)s;
+  float* Wt = nullptr;
+  const bool need_wt = rhs->kind == NDCN_RHS_NDCN && !(rhs->flags & NDCN_F_NO_CONTROL) &&
+                       (rhs->H == 256 || rhs->H == 128 || rhs->H == 64 || rhs->H == 32);
+  if (need_wt) {
+    if (!rhs->W) return NDCN_E_ARG;
+    CU_TRY(cudaMallocAsync((void**)&Wt, sizeof(float) * rhs->H * rhs->H, st));
+    const int n = rhs->H * rhs->H;
+    k_transpose<<<(n + 255) / 256, 256, 0, st>>>(rhs->W, Wt, rhs->H);
+  }
+  RhsBinding b{g, rhs, Wt, nullptr, 0, 148};
+  int rc = launch_stage(b, pp(const_cast<float*>(x)), store_only(out), nullptr, st);
+  if (Wt) cudaFreeAsync(Wt, st);
+  return rc;
+}
+
+extern "C" int ndcn_spmm_f32(const ndcn_graph_t* g, const float* x, float* y, int32_t H, ndcn_stream_t s) {
+  ndcn_rhs_desc_t r;
+  std::memset(&r, 0, sizeof(r));
+  r.kind = NDCN_RHS_NDCN;
+  r.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+  r.H = H;
+  return ndcn_rhs_eval_f32(g, &r, x, y, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// solver object
+// ---------------------------------------------------------------------------------------
+static size_t state_bytes(int64_t rows, int H) { return align_up((size_t)rows * H * sizeof(float), 256); }
+
+extern "C" size_t ndcn_solver_workspace_bytes(int64_t n_rows, int64_t n_cols, int32_t H, int32_t method) {
+  (void)method;
+  if (n_cols < n_rows) n_cols = n_rows;
+  size_t b = 0;
+  b += 4 * state_bytes(n_cols, H);                      // Y[2], YS[2]
+  b += 7 * state_bytes(n_rows, H);                      // KF[2], K[5]
+  b += align_up(sizeof(float) * (size_t)H * H, 256);    // W^T
+  return b + 256;
+}
+
+extern "C" int ndcn_solver_create(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, int32_t method,
+                                  void* workspace, size_t workspace_bytes, ndcn_solver_t** out) {
+  if (!g || !rhs || !out || !workspace) return NDCN_E_ARG;
+  if (method < NDCN_EULER || method > NDCN_DOPRI5) return NDCN_E_METHOD;
+  if (rhs->H < 1) return NDCN_E_ARG;
+  const int64_t n_rows = g->v.n_rows, n_cols = g->v.n_cols;
+  if (workspace_bytes < ndcn_solver_workspace_bytes(n_rows, n_cols, rhs->H, method)) return NDCN_E_WORKSPACE;
+  ndcn_solver* sv = new (std::nothrow) ndcn_solver();
+  if (!sv) return NDCN_E_ARG;
+  sv->g = g;
+  sv->rhs = *rhs;
+  sv->method = method;
+  sv->n_rows = n_rows;
+  sv->n_cols = n_cols;
+  sv->H = rhs->H;
+  sv->numel = n_rows * rhs->H;
+  sv->numel_src = n_cols * rhs->H;
+  unsigned char* p = (unsigned char*)align_up((size_t)workspace, 256);
+  auto take = [&](size_t bytes) {
+    float* r = (float*)p;
+    p += bytes;
+    return r;
+  };
+  for (int i = 0; i < 2; ++i) sv->Y[i] = take(state_bytes(n_cols, sv->H));
+  for (int i = 0; i < 2; ++i) sv->YS[i] = take(state_bytes(n_cols, sv->H));
+  for (int i = 0; i < 2; ++i) sv->KF[i] = take(state_bytes(n_rows, sv->H));
+  for (int i = 0; i < 5; ++i) sv->K[i] = take(state_bytes(n_rows, sv->H));
+  sv->Wt = take(align_up(sizeof(float) * (size_t)sv->H * sv->H, 256));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sv->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  sv->max_partials = max_partials_for(n_rows, sv->H);
+  int rc = (int)cudaMalloc((void**)&sv->partials, sizeof(double) * 2 * sv->max_partials);
+  if (!rc) rc = (int)cudaMalloc((void**)&sv->xchg, sizeof(double) * 4);
+  if (!rc) rc = (int)cudaMalloc((void**)&sv->t_stage, sizeof(float) * 4);
+  if (!rc) rc = (int)cudaMalloc((void**)&sv->ctrl, sizeof(Ctrl));
+  if (!rc) rc = (int)cudaMallocHost((void**)&sv->ctrl_host, sizeof(Ctrl));
+  if (rc) {
+    ndcn_solver_destroy(sv);
+    return rc;
+  }
+  *out = sv;
+  return NDCN_OK;
+}
+
+extern "C" int ndcn_solver_destroy(ndcn_solver_t* sv) {
+  if (!sv) return NDCN_OK;
+  if (sv->partials) cudaFree(sv->partials);
+  if (sv->xchg) cudaFree(sv->xchg);
+  if (sv->t_stage) cudaFree(sv->t_stage);
+  if (sv->t_out) cudaFree(sv->t_out);
+  if (sv->ctrl) cudaFree(sv->ctrl);
+  if (sv->ctrl_host) cudaFreeHost(sv->ctrl_host);
+  delete sv;
+  return NDCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Driver {
+  ndcn_solver* sv;
+  const ndcn_solve_opts_t* o;
+  cudaStream_t st;
+  RhsBinding bind;
+  bool vec_ok;       // all elementwise buffers are 16-byte aligned and numel % 4 == 0 handled
+  int64_t nfe = 0;
+
+  EpiArgs blank() const {
+    EpiArgs e;
+    std::memset(&e, 0, sizeof(e));
+    return e;
+  }
+
+  int exchange(float* buf) {  // fill halo rows of a gather source (multi-GPU hook)
+    if (o->exchange && sv->n_cols > sv->n_rows) return o->exchange(o->exchange_user, 0, buf);
+    return 0;
+  }
+
+  // one RHS evaluation fused with epilogue e. `src_host` is the buffer the host knows to be the
+  // source (needed for the exchange/callback hooks; the kernels themselves select by parity).
+  int stage(PtrPair src, float* src_host, EpiArgs e, float* k_host, int* n_partials = nullptr) {
+    RC_TRY(exchange(src_host));
+    nfe += 1;
+    if (sv->rhs.kind == NDCN_RHS_CALLBACK) {
+      if (!sv->rhs.callback || !k_host) return NDCN_E_ARG;
+      RC_TRY(sv->rhs.callback(sv->rhs.callback_user, src_host, k_host, sv->t_stage));
+      // epilogue on the k the callback produced; k is already where it belongs
+      EpiArgs e2 = e;
+      e2.k_out = pp(nullptr);
+      return epi_only(pp(k_host), e2, n_partials);
+    }
+    sv->launches += 1;
+    return launch_stage(bind, src, e, n_partials, st);
+  }
+
+  int epi_only(PtrPair k_in, EpiArgs e, int* n_partials = nullptr) {
+    e.partials = sv->partials;
+    const int grid = grid_for_elems(sv->numel, sv->sm_count);
+    if (n_partials) *n_partials = grid;
+    sv->launches += 1;
+    k_epi_only<<<grid, kStageThreads, 0, st>>>(k_in, sv->numel, e, vec_ok ? 1 : 0);
+    return (int)cudaGetLastError();
+  }
+
+  int poll() {
+    CU_TRY(cudaMemcpyAsync(sv->ctrl_host, sv->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+  }
+};
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// ---- fixed grid: euler / midpoint / rk4 (3/8) -------------------------------------------
+// solvers.py:79-99 with the default grid (= t cast to the state's dtype)
+int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* out) {
+  ndcn_solver* sv = d.sv;
+  cudaStream_t st = d.st;
+  const bool terminal = (d.o->flags & NDCN_O_TERMINAL_ONLY) != 0;
+  const bool multi = sv->n_cols > sv->n_rows;
+  const bool in_slab = !terminal && !multi;  // the output slab doubles as state storage
+  const size_t bytes = sizeof(float) * (size_t)sv->numel;
+  float* cur;
+  if (in_slab) {
+    CU_TRY(cudaMemcpyAsync(out, y0, bytes, cudaMemcpyDeviceToDevice, st));
+    cur = out;
+  } else {
+    CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!terminal) CU_TRY(cudaMemcpyAsync(out, y0, bytes, cudaMemcpyDeviceToDevice, st));
+    cur = sv->Y[0];
+  }
+  for (int i = 0; i + 1 < n_t; ++i) {
+    const float t0 = (float)t[i], t1 = (float)t[i + 1];
+    const float dt = t1 - t0;  // fp32 subtraction of fp32-rounded times (solvers.py:81,89)
+    float* nxt = in_slab ? out + (size_t)(i + 1) * sv->numel : sv->Y[(i + 1) & 1];
+    EpiArgs e = d.blank();
+    e.dt_src = DT_HOST;
+    e.dt_host = dt;
+    e.y0 = pp(cur);
+    if (sv->method == NDCN_EULER) {  // fixed_grid.py:7-8
+      e.mode = EPI_LINCOMB;
+      e.beta[0] = 1.0f;
+      e.y_out = pp(nxt);
+      RC_TRY(d.stage(pp(cur), cur, e, sv->K[0]));
+    } else if (sv->method == NDCN_MIDPOINT) {  // fixed_grid.py:17-20
+      e.mode = EPI_LINCOMB;
+      e.beta[0] = 0.5f;  // y + f*dt/2 == y + (dt*0.5)*f bit for bit (power-of-two scaling)
+      e.y_out = pp(sv->YS[0]);
+      RC_TRY(d.stage(pp(cur), cur, e, sv->K[0]));
+      e.beta[0] = 1.0f;
+      e.y_out = pp(nxt);
+      RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[0]));
+    } else {  // rk_common.py:72-78
+      e.mode = EPI_RK4_1;
+      e.k_out = pp(sv->K[0]);
+      e.y_out = pp(sv->YS[0]);
+      RC_TRY(d.stage(pp(cur), cur, e, sv->K[0]));
+      e.mode = EPI_RK4_2;
+      e.k_out = pp(sv->K[1]);
+      e.kprev[0] = pp(sv->K[0]);
+      e.y_out = pp(sv->YS[1]);
+      RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[1]));
+      e.mode = EPI_RK4_3;
+      e.k_out = pp(sv->K[2]);
+      e.kprev[1] = pp(sv->K[1]);
+      e.y_out = pp(sv->YS[0]);
+      RC_TRY(d.stage(pp(sv->YS[1]), sv->YS[1], e, sv->K[2]));
+      e.mode = EPI_RK4_4;
+      e.k_out = pp(nullptr);
+      e.kprev[2] = pp(sv->K[2]);
+      e.y_out = pp(nxt);
+      RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[3]));
+    }
+    if (!in_slab && !terminal)
+      CU_TRY(cudaMemcpyAsync(out + (size_t)(i + 1) * sv->numel, nxt, bytes, cudaMemcpyDeviceToDevice, st));
+    cur = nxt;
+    sv->ctrl_host->n_accept += 1;
+  }
+  if (terminal) CU_TRY(cudaMemcpyAsync(out, cur, bytes, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  sv->ctrl_host->t1 = t[n_t - 1];
+  return 0;
+}
+
+// ---- dopri5 ------------------------------------------------------------------------------
+struct Dopri {
+  Driver& d;
+  ndcn_solver* sv;
+  float beta32[6][8];
+  float err32[8];
+  EmitArgs emit;
+  bool host_parity;  // hooks need the host to know the buffer parity: poll every attempt
+  int par = 0;
+
+  explicit Dopri(Driver& dr) : d(dr), sv(dr.sv) {
+    std::memset(beta32, 0, sizeof(beta32));
+    std::memset(err32, 0, sizeof(err32));
+    for (int s = 0; s < 6; ++s)
+      for (int j = 0; j <= s; ++j) beta32[s][j] = (float)kDpBeta[s][j];
+    for (int j = 0; j < 7; ++j) err32[j] = (float)kDpErr[j];
+  }
+
+  int reduce_and_control(int n_partials) {
+    const bool multi = d.o->exchange != nullptr;
+    if (!multi) {
+      sv->launches += 1;
+      k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 0);
+    } else {
+      sv->launches += 2;
+      k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 1);
+      RC_TRY(d.o->exchange(d.o->exchange_user, 1, sv->xchg));
+      k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 2);
+    }
+    return (int)cudaGetLastError();
+  }
+
+  int attempt() {
+    float* Yp = sv->Y[par];
+    float* Yq = sv->Y[par ^ 1];
+    float* KFq = sv->KF[par ^ 1];
+    const PtrPair Ycur = pp(sv->Y[0], sv->Y[1]), Yoth = pp(sv->Y[1], sv->Y[0]);
+    const PtrPair KFcur = pp(sv->KF[0], sv->KF[1]), KFoth = pp(sv->KF[1], sv->KF[0]);
+    (void)Yp;
+    EpiArgs e = d.blank();
+    e.ctrl = sv->ctrl;
+    e.dt_src = DT_CTRL;
+    e.y0 = Ycur;
+    // stage input 1: y0 + (dt*b10) k0, k0 = FSAL derivative; also the finite-state guard
+    e.mode = EPI_LINCOMB;
+    e.n_prev = 0;
+    e.beta[0] = beta32[0][0];
+    e.check_finite = 1;
+    e.y_out = pp(sv->YS[0]);
+    RC_TRY(d.epi_only(KFcur, e));
+    e.check_finite = 0;
+    e.kprev[0] = KFcur;
+    for (int s = 1; s <= 5; ++s) {
+      float* src = sv->YS[(s - 1) & 1];
+      e.n_prev = s;
+      for (int j = 0; j < 8; ++j) e.beta[j] = beta32[s][j];
+      e.k_out = pp(sv->K[s - 1]);
+      if (s >= 2) e.kprev[s - 1] = pp(sv->K[s - 2]);
+      e.y_out = (s < 5) ? pp(sv->YS[s & 1]) : Yoth;  // stage 5 forms y1 (FSAL: c_sol == beta[-1])
+      RC_TRY(d.stage(pp(src), src, e, sv->K[s - 1]));
+    }
+    // stage 6: k7 = f(y1) + error estimate
+    e.mode = EPI_ERR;
+    e.n_prev = 6;
+    for (int j = 0; j < 8; ++j) e.beta[j] = err32[j];
+    e.kprev[5] = pp(sv->K[4]);
+    e.k_out = KFoth;
+    e.y_out = pp(nullptr);
+    e.y1 = Yoth;
+    e.rtol = (float)d.o->rtol;
+    e.atol = (float)d.o->atol;
+    int n_partials = 0;
+    RC_TRY(d.stage(Yoth, Yq, e, KFq, &n_partials));
+    RC_TRY(reduce_and_control(n_partials));
+    sv->launches += 1;
+    k_emit<<<grid_for_elems(sv->numel, sv->sm_count), kStageThreads, 0, d.st>>>(emit, d.vec_ok ? 1 : 0);
+    return (int)cudaGetLastError();
+  }
+
+  int init_scalar(int n_partials, int phase, double t_first) {
+    const bool multi = d.o->exchange != nullptr;
+    if (!multi) {
+      sv->launches += 1;
+      k_init_scalar<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, phase, t_first, sv->xchg, 0);
+    } else {
+      sv->launches += 2;
+      k_init_scalar<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, phase, t_first, sv->xchg, 1);
+      RC_TRY(d.o->exchange(d.o->exchange_user, 1, sv->xchg));
+      k_init_scalar<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, phase, t_first, sv->xchg, 2);
+    }
+    return (int)cudaGetLastError();
+  }
+
+  int run(const float* y0, const double* t, int n_t, float* out) {
+    cudaStream_t st = d.st;
+    const bool terminal = (d.o->flags & NDCN_O_TERMINAL_ONLY) != 0;
+    const bool forced = (d.o->flags & NDCN_O_FORCED_DT) != 0;
+    const size_t bytes = sizeof(float) * (size_t)sv->numel;
+    host_parity = d.o->exchange != nullptr || sv->rhs.kind == NDCN_RHS_CALLBACK;
+
+    // requested times -> device (float64, already fp32-rounded by ODEBlock when it applies)
+    if (sv->t_cap < n_t) {
+      if (sv->t_out) cudaFree(sv->t_out);
+      sv->t_cap = std::max(n_t, 128);
+      CU_TRY(cudaMalloc((void**)&sv->t_out, sizeof(double) * sv->t_cap));
+    }
+    CU_TRY(cudaMemcpyAsync(sv->t_out, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
+
+    Ctrl& h = *sv->ctrl_host;
+    std::memset(&h, 0, sizeof(h));
+    h.t0 = h.t1 = t[0];
+    h.rtol = d.o->rtol;
+    h.atol = d.o->atol;
+    // _convert_to_tensor(0.9, float64) goes through an fp32 tensor first (misc.py:39-47)
+    h.safety = (double)(float)(d.o->safety > 0 ? d.o->safety : 0.9);
+    h.ifactor = (double)(float)(d.o->ifactor > 0 ? d.o->ifactor : 10.0);
+    h.dfactor = (double)(float)(d.o->dfactor > 0 ? d.o->dfactor : 0.2);
+    h.forced = forced ? 1 : 0;
+    h.forced_dt = d.o->forced_dt;
+    h.dt = forced ? d.o->forced_dt : 0.0;
+    h.first_step = h.dt;
+    h.numel_global = (double)sv->numel;  // multi-GPU: overwritten below through the hook
+    h.max_num_steps = d.o->max_num_steps > 0 ? d.o->max_num_steps : 2147483647LL;
+    h.next_out = 1;
+    h.n_out = n_t;
+    h.emit_lo = h.emit_hi = 1;
+    h.terminal_only = terminal ? 1 : 0;
+    if (d.o->exchange) {
+      // global element count = all-reduce of the local one (same hook, what = 1)
+      double tmp[2] = {(double)sv->numel, 0.0};
+      CU_TRY(cudaMemcpyAsync(sv->xchg, tmp, sizeof(tmp), cudaMemcpyHostToDevice, st));
+      RC_TRY(d.o->exchange(d.o->exchange_user, 1, sv->xchg));
+      CU_TRY(cudaMemcpyAsync(tmp, sv->xchg, sizeof(tmp), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      h.numel_global = tmp[0];
+    }
+    CU_TRY(cudaMemcpyAsync(sv->ctrl, &h, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));  // ctrl_host is reused as the poll target below
+
+    CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!terminal) CU_TRY(cudaMemcpyAsync(out, y0, bytes, cudaMemcpyDeviceToDevice, st));
+
+    emit.ctrl = sv->ctrl;
+    emit.t_out = sv->t_out;
+    emit.y0 = pp(sv->Y[0], sv->Y[1]);
+    emit.y1 = pp(sv->Y[1], sv->Y[0]);
+    emit.k0 = pp(sv->KF[0], sv->KF[1]);
+    emit.k6 = pp(sv->KF[1], sv->KF[0]);
+    for (int j = 0; j < 5; ++j) emit.k[j] = sv->K[j];
+    for (int j = 0; j < 7; ++j) emit.c_mid[j] = (float)kDpMid[j];
+    emit.out = out;
+    emit.numel = sv->numel;
+
+    // f0 = func(t0, y0)     dopri5.py:78
+    RC_TRY(d.stage(pp(sv->Y[0]), sv->Y[0], store_only(sv->KF[0]), sv->KF[0]));
+    if (!forced) {
+      // _select_initial_step(order=4)     dopri5.py:80, misc.py:84-143
+      const int grid = grid_for_elems(sv->numel, sv->sm_count);
+      sv->launches += 1;
+      k_init_norms<<<grid, kStageThreads, 0, st>>>(sv->Y[0], sv->KF[0], nullptr, sv->numel, (float)d.o->rtol,
+                                                    (float)d.o->atol, 0, sv->partials);
+      RC_TRY(init_scalar(grid, 0, t[0]));
+      EpiArgs e = d.blank();
+      e.ctrl = sv->ctrl;
+      e.dt_src = DT_CTRL_H0;
+      e.mode = EPI_LINCOMB;
+      e.beta[0] = 1.0f;
+      e.y0 = pp(sv->Y[0]);
+      e.y_out = pp(sv->YS[0]);
+      RC_TRY(d.epi_only(pp(sv->KF[0]), e));  // y0 + h0*f0
+      RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], store_only(sv->K[0]), sv->K[0]));
+      sv->launches += 1;
+      k_init_norms<<<grid, kStageThreads, 0, st>>>(sv->Y[0], sv->KF[0], sv->K[0], sv->numel, (float)d.o->rtol,
+                                                    (float)d.o->atol, 1, sv->partials);
+      RC_TRY(init_scalar(grid, 1, t[0]));
+    }
+    CU_TRY(cudaGetLastError());
+
+    // attempts are enqueued in growing batches; kernels of attempts past the end are no-ops
+    int batch = host_parity ? 1 : 2;
+    for (;;) {
+      for (int i = 0; i < batch; ++i) RC_TRY(attempt());
+      RC_TRY(d.poll());
+      const Ctrl& c = *sv->ctrl_host;
+      par = c.parity;
+      if (c.done) break;
+      if (!host_parity) batch = std::min(batch * 2, 16);
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+
+extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t, float* out,
+                               const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats, ndcn_stream_t s) {
+  if (!sv || !y0 || !t_host || !out || !opts || n_t < 1) return NDCN_E_ARG;
+  if (opts->method != sv->method) return NDCN_E_METHOD;
+  for (int i = 0; i + 1 < n_t; ++i)
+    if (!(t_host[i + 1] > t_host[i])) return NDCN_E_ARG;  // misc.py:59-60
+  cudaStream_t st = (cudaStream_t)s;
+  sv->launches = 0;
+  Driver d{sv, opts, st, RhsBinding{sv->g, &sv->rhs, sv->Wt, sv->partials, sv->max_partials, sv->sm_count}, false, 0};
+  d.vec_ok = aligned16(out) && aligned16(y0) && (sv->numel % 4 == 0);
+  std::memset(sv->ctrl_host, 0, sizeof(Ctrl));
+
+  const bool fast_h = sv->H == 256 || sv->H == 128 || sv->H == 64 || sv->H == 32;
+  if (sv->rhs.kind == NDCN_RHS_NDCN && !(sv->rhs.flags & NDCN_F_NO_CONTROL) && fast_h) {
+    const int n = sv->H * sv->H;
+    k_transpose<<<(n + 255) / 256, 256, 0, st>>>(sv->rhs.W, sv->Wt, sv->H);
+    sv->launches += 1;
+  }
+  if (sv->rhs.kind == NDCN_RHS_NDCN && fast_h && !(aligned16(out) && aligned16(y0))) return NDCN_E_ARG;
+
+  int rc = 0;
+  if (n_t == 1) {
+    rc = (int)cudaMemcpyAsync(out, y0, sizeof(float) * (size_t)sv->numel, cudaMemcpyDeviceToDevice, st);
+    if (!rc) rc = (int)cudaStreamSynchronize(st);
+  } else if (sv->method == NDCN_DOPRI5) {
+    Dopri dp(d);
+    rc = dp.run(y0, t_host, n_t, out);
+  } else {
+    rc = run_fixed_grid(d, y0, t_host, n_t, out);
+  }
+  if (stats) {
+    const Ctrl& c = *sv->ctrl_host;
+    stats->nfe = d.nfe;
+    stats->n_accepted = c.n_accept;
+    stats->n_rejected = c.n_reject;
+    stats->n_launches = sv->launches;
+    stats->first_step = c.first_step;
+    stats->last_dt = c.dt;
+    stats->t_final = c.t1;
+    stats->status = rc < 0 ? rc : c.status;
+    stats->reserved = 0;
+  }
+  if (rc != 0) return rc;
+  return sv->ctrl_host->status;
+}
+
+// ---------------------------------------------------------------------------------------
+// solver algebra as stand-alone kernels
+// ---------------------------------------------------------------------------------------
+extern "C" int ndcn_rk_combine_f32(float* out, const float* y0, const float* const* k_host_ptrs,
+                                   const double* beta_host, int32_t n_k, float dt, int64_t numel, ndcn_stream_t s) {
+  if (!out || !y0 || !k_host_ptrs || !beta_host || n_k < 1 || n_k > 7 || numel < 0) return NDCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)s;
+  EpiArgs e;
+  std::memset(&e, 0, sizeof(e));
+  e.mode = EPI_LINCOMB;
+  e.n_prev = n_k - 1;
+  e.dt_src = DT_HOST;
+  e.dt_host = dt;
+  e.y0 = pp(const_cast<float*>(y0));
+  e.y_out = pp(out);
+  for (int j = 0; j < n_k - 1; ++j) e.kprev[j] = pp(const_cast<float*>(k_host_ptrs[j]));
+  for (int j = 0; j < n_k; ++j) e.beta[j] = (float)beta_host[j];
+  bool vec = aligned16(out) && aligned16(y0) && numel % 4 == 0;
+  for (int j = 0; j < n_k; ++j) vec = vec && aligned16(k_host_ptrs[j]);
+  k_epi_only<<<grid_for_elems(numel, 148), kStageThreads, 0, st>>>(pp(const_cast<float*>(k_host_ptrs[n_k - 1])), numel, e,
+                                                                  vec ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ndcn_error_ratio_f32(const float* err, const float* y0, const float* y1, double rtol, double atol,
+                                    int64_t numel, double* sum_out_dev, ndcn_stream_t s) {
+  if (!err || !y0 || !y1 || !sum_out_dev || numel < 0) return NDCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)s;
+  const int grid = grid_for_elems(numel, 148);
+  double* partials = nullptr;
+  CU_TRY(cudaMallocAsync((void**)&partials, sizeof(double) * grid, st));
+  k_error_ratio<<<grid, kStageThreads, 0, st>>>(err, y0, y1, numel, (float)rtol, (float)atol, partials);
+  k_sum_partials<<<1, kStageThreadsCtl, 0, st>>>(partials, grid, sum_out_dev);
+  cudaFreeAsync(partials, st);
+  return (int)cudaGetLastError();
+}
+
+extern "C" const char* ndcn_version(void) { return "ndcn_b200 0.1.0 (sm_100a)"; }
+extern "C" int ndcn_sm_arch(void) { return 100; }

@@ -1,0 +1,330 @@
+// Shared device-side definitions for libndcn_b200 (sm_100a).
+//
+// Rounding discipline: everything that mirrors the reference's *solver algebra*
+// (torchdiffeq/_impl/{rk_common,misc,interp,dopri5}.py) is written with explicit
+// __fmul_rn/__fadd_rn so that nvcc cannot contract it into FMAs: the reference issues one
+// full-tensor mul and one full-tensor add per term, each rounded to fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ndcn_b200.h"
+
+namespace ndcn {
+
+constexpr int kStageThreadsCtl = 256;  // block size of the single-block scalar kernels
+constexpr int kStageThreads = 256;     // block size of every stage / elementwise kernel
+constexpr int kWarpsPerCta = kStageThreads / 32;
+
+// ------------------------------------------------------------------------------------
+// Device-resident controller block: the adaptive solver's scalars never visit the host
+// between polls (the reference syncs >=3 times per step, dopri5.py:88,100-102,109).
+// ------------------------------------------------------------------------------------
+struct Ctrl {
+  double t0, t1, dt;                 // _RungeKuttaState.t0/.t1/.dt  (rk_common.py:8-19), float64
+  double emit_t0, emit_t1, emit_dt;  // interval of the step whose dense output is pending
+  double rtol, atol;
+  double safety, ifactor, dfactor;   // dopri5.py:71-73 (already fp32-rounded by the host)
+  double forced_dt;
+  double first_step;
+  double sum_sq;                     // last sum of squared error ratios (diagnostic)
+  double numel_global;               // element count of the (global) state, for the mean
+  long long n_accept, n_reject, n_attempt;
+  long long steps_this_interval, max_num_steps;
+  float h0, d0, d1, msr_last;        // _select_initial_step scratch (misc.py:84-143), fp32
+  int parity;                        // which of Y[2]/KF[2] holds y0/f0
+  int done, status, forced;
+  int next_out, n_out;               // next requested time index to emit
+  int emit_lo, emit_hi, emit_parity; // outputs [emit_lo, emit_hi) fall in the pending step
+  int terminal_only;
+};
+
+struct PtrPair {  // buffer chosen by Ctrl::parity (both equal for parity-free buffers)
+  float* p[2];
+};
+
+enum EpiMode : int {
+  EPI_STORE = 0,    // k_out = k
+  EPI_LINCOMB = 1,  // y_out = y0 + sum_j (dt*beta_j) k_j, fresh k last   (rk_common.py:50)
+  EPI_ERR = 2,      // dopri5 last stage: error estimate + squared-ratio partial sums
+  EPI_RK4_1 = 3,    // y + dt*k1/3                                (rk_common.py:75)
+  EPI_RK4_2 = 4,    // y + dt*(k1/-3 + k2)                        (rk_common.py:76)
+  EPI_RK4_3 = 5,    // y + dt*(k1 - k2 + k3)                      (rk_common.py:77)
+  EPI_RK4_4 = 6,    // y + (k1 + 3k2 + 3k3 + k4)*(dt/8)           (rk_common.py:78, solvers.py:91)
+};
+
+enum DtSrc : int { DT_HOST = 0, DT_CTRL = 1, DT_CTRL_H0 = 2 };
+
+struct EpiArgs {
+  int mode;
+  int n_prev;         // previous stages read from HBM (<= 6)
+  int dt_src;         // DtSrc
+  int check_finite;   // also flag non-finite y0 (dopri5.py:101-102)
+  PtrPair k_out;      // may be {0,0}
+  PtrPair y_out;
+  PtrPair y0;
+  PtrPair y1;         // EPI_ERR only
+  PtrPair kprev[6];
+  float beta[8];      // fp32(beta_j); coefficient = fp32(dt) * beta_j   (misc.py:25)
+  Ctrl* ctrl;         // may be null (fixed-grid solvers, stand-alone ops)
+  float dt_host;
+  float rtol, atol;
+  double* partials;   // [gridDim.x] per-CTA partial sums (EPI_ERR)
+};
+
+struct EpiCtx {  // EpiArgs resolved against the controller, per thread
+  int mode, n_prev;
+  float* k_out;
+  float* y_out;
+  const float* y0;
+  const float* y1;
+  const float* kprev[6];
+  float coef[8];
+  float coef_fresh;  // coefficient of the k still in registers (= coef[n_prev])
+  float dt;
+  float rtol, atol;
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// kernel parameters live in constant memory: select, do not index dynamically (that would
+// force a local-memory copy of the whole argument struct)
+__device__ __forceinline__ float* sel(const PtrPair& q, int par) { return par ? q.p[1] : q.p[0]; }
+
+// returns false when the solve is already finished (kernel should exit)
+__device__ __forceinline__ bool epi_resolve(const EpiArgs& a, EpiCtx& c) {
+  int par = 0;
+  float dt = a.dt_host;
+  if (a.ctrl != nullptr) {
+    const volatile Ctrl* ct = a.ctrl;
+    if (ct->done) return false;
+    par = ct->parity;
+    if (a.dt_src == DT_CTRL) dt = (float)ct->dt;  // dt.type(fp32)   rk_common.py:46
+    else if (a.dt_src == DT_CTRL_H0) dt = ct->h0;
+  }
+  c.mode = a.mode;
+  c.n_prev = a.n_prev;
+  c.k_out = sel(a.k_out, par);
+  c.y_out = sel(a.y_out, par);
+  c.y0 = sel(a.y0, par);
+  c.y1 = sel(a.y1, par);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) c.kprev[j] = sel(a.kprev[j], par);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c.coef[j] = fmul(dt, a.beta[j]);
+  c.coef_fresh = fmul(dt, a.beta[a.n_prev & 7]);
+  c.dt = dt;
+  c.rtol = a.rtol;
+  c.atol = a.atol;
+  return true;
+}
+
+// ---- vector load/store helpers (VW in {1,2,4}) ---------------------------------------
+template <int VW>
+__device__ __forceinline__ void ldv(const float* __restrict__ p, float (&v)[VW]) {
+  if constexpr (VW == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VW == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = *p;
+  }
+}
+template <int VW>
+__device__ __forceinline__ void ldv_stream(const float* __restrict__ p, float (&v)[VW]) {
+  if constexpr (VW == 4) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VW == 2) {
+    float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldcs(p);
+  }
+}
+template <int VW>
+__device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[VW]) {
+  if constexpr (VW == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (VW == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else {
+    *p = v[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// The stage epilogue: consumes freshly computed k values (still in registers) for VW
+// consecutive elements starting at element offset `off`.
+// ------------------------------------------------------------------------------------
+template <int VW>
+__device__ __forceinline__ void epi_apply(const EpiCtx& c, int64_t off, const float (&k)[VW],
+                                          double& err_acc) {
+  if (c.k_out != nullptr) stv<VW>(c.k_out + off, k);
+  if (c.mode == EPI_STORE) return;
+
+  if (c.mode == EPI_LINCOMB) {
+    float acc[VW];
+    float y0v[VW];
+    ldv_stream<VW>(c.y0 + off, y0v);
+    if (c.n_prev == 0) {
+#pragma unroll
+      for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], k[i]);
+    } else {
+      float kv[VW];
+      ldv_stream<VW>(c.kprev[0] + off, kv);
+#pragma unroll
+      for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], kv[i]);
+#pragma unroll
+      for (int j = 1; j < 6; ++j) {
+        if (j < c.n_prev) {
+          ldv_stream<VW>(c.kprev[j] + off, kv);
+#pragma unroll
+          for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], kv[i]));
+        }
+      }
+      const float cf = c.coef_fresh;
+#pragma unroll
+      for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(cf, k[i]));
+    }
+    float out[VW];
+#pragma unroll
+    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], acc[i]);
+    stv<VW>(c.y_out + off, out);
+    return;
+  }
+
+  if (c.mode == EPI_ERR) {
+    // err = sum_j (dt*c_err_j) k_j (7 terms, k6 fresh)           rk_common.py:60
+    // ratio = err / (atol + rtol*max(|y0|,|y1|)); sum ratio^2      misc.py:146-157
+    float acc[VW], kv[VW], y0v[VW], y1v[VW];
+    ldv_stream<VW>(c.kprev[0] + off, kv);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], kv[i]);
+#pragma unroll
+    for (int j = 1; j < 6; ++j) {
+      ldv_stream<VW>(c.kprev[j] + off, kv);
+#pragma unroll
+      for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], kv[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[6], k[i]));
+    ldv_stream<VW>(c.y0 + off, y0v);
+    ldv<VW>(c.y1 + off, y1v);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) {
+      float tol = fadd(c.atol, fmul(c.rtol, fmaxf(fabsf(y0v[i]), fabsf(y1v[i]))));
+      float r = fdiv(acc[i], tol);
+      float r2 = fmul(r, r);
+      // torch.max propagates NaN, fmaxf does not: keep the poison visible to the controller
+      if (!(r2 == r2) || y0v[i] != y0v[i] || y1v[i] != y1v[i]) r2 = __int_as_float(0x7fc00000);
+      err_acc += (double)r2;
+    }
+    return;
+  }
+
+  // ---- RK4 (3/8 rule), literal operation order of rk_common.py:72-78 ----
+  float y0v[VW], out[VW];
+  ldv_stream<VW>(c.y0 + off, y0v);
+  const float dt = c.dt;
+  if (c.mode == EPI_RK4_1) {
+#pragma unroll
+    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], fdiv(fmul(dt, k[i]), 3.0f));
+  } else if (c.mode == EPI_RK4_2) {
+    float k1[VW];
+    ldv_stream<VW>(c.kprev[0] + off, k1);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], fmul(dt, fadd(fdiv(k1[i], -3.0f), k[i])));
+  } else if (c.mode == EPI_RK4_3) {
+    float k1[VW], k2[VW];
+    ldv_stream<VW>(c.kprev[0] + off, k1);
+    ldv_stream<VW>(c.kprev[1] + off, k2);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], fmul(dt, fadd(fsub(k1[i], k2[i]), k[i])));
+  } else {  // EPI_RK4_4
+    float k1[VW], k2[VW], k3[VW];
+    ldv_stream<VW>(c.kprev[0] + off, k1);
+    ldv_stream<VW>(c.kprev[1] + off, k2);
+    ldv_stream<VW>(c.kprev[2] + off, k3);
+    const float dt8 = fdiv(dt, 8.0f);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) {
+      float s = fadd(fadd(fadd(k1[i], fmul(3.0f, k2[i])), fmul(3.0f, k3[i])), k[i]);
+      out[i] = fadd(y0v[i], fmul(s, dt8));
+    }
+  }
+  stv<VW>(c.y_out + off, out);
+}
+
+// per-CTA reduction of the error partials; every CTA writes its slot (zeros included)
+__device__ __forceinline__ void epi_finish_block(const EpiArgs& a, double err_acc) {
+  if (a.mode != EPI_ERR) return;
+  __shared__ double s_red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarp = (blockDim.x + 31) >> 5;
+  if (lane == 0) s_red[warp] = err_acc;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < nwarp ? s_red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) a.partials[blockIdx.x] = v;
+  }
+}
+
+struct GraphView {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  int64_t n_rows, n_cols, nnz;
+};
+
+// ---- mbarrier / bulk-copy (TMA, 1-D) PTX wrappers --------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// cp.async.bulk (SASS: UBLKCP): contiguous global -> shared, completion on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace ndcn

@@ -1,0 +1,343 @@
+// Device-side step control for dopri5 and the dense-output / initial-step kernels.
+// Reference: torchdiffeq/_impl/dopri5.py:58-122, misc.py:84-170, interp.py:5-65.
+#pragma once
+#include "ndcn_common.cuh"
+
+namespace ndcn {
+
+// deterministic fixed-order sum of the per-CTA partials (one block)
+__device__ __forceinline__ double block_sum_partials(const double* __restrict__ partials, int n) {
+  __shared__ double s_tmp[kStageThreadsCtl];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+  s_tmp[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_tmp[threadIdx.x] += s_tmp[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = s_tmp[0];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Accept / reject + next step size.  One block; thread 0 does the float64 scalar work.
+// `reduce_stage`: 0 = sum partials and (single GPU) decide immediately;
+//                 1 = only sum partials into xchg[0..1] (multi-GPU: the host hook all-reduces);
+//                 2 = decide from xchg[0] (after the all-reduce).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStageThreadsCtl) k_controller(Ctrl* ctrl, const double* partials, int n_partials,
+                                                                 const double* t_out, double* xchg, int reduce_stage) {
+  if (((volatile Ctrl*)ctrl)->done) {
+    // attempts enqueued past the end are no-ops: also retire the already-emitted outputs
+    if (threadIdx.x == 0) ctrl->emit_lo = ctrl->emit_hi;
+    return;
+  }
+  if (((volatile Ctrl*)ctrl)->status != 0) {  // e.g. non-finite state flagged by the pre-stage
+    if (threadIdx.x == 0) { ctrl->done = 1; ctrl->emit_lo = ctrl->emit_hi; }
+    return;
+  }
+  double sum = 0.0;
+  if (reduce_stage != 2) sum = block_sum_partials(partials, n_partials);
+  if (threadIdx.x != 0) return;
+  if (reduce_stage == 1) {
+    xchg[0] = sum;
+    xchg[1] = 0.0;
+    return;
+  }
+  if (reduce_stage == 2) sum = xchg[0];
+
+  Ctrl& c = *ctrl;
+  c.sum_sq = sum;
+  c.n_attempt += 1;
+  // torch.mean of the squared ratios, an fp32 scalar   (misc.py:155-156)
+  const float msr = (float)(sum / c.numel_global);
+  c.msr_last = msr;
+  const bool accept = c.forced ? true : (msr <= 1.0f);  // dopri5.py:109
+  const double dt = c.dt;
+  const double t_start = c.t1;
+  c.emit_lo = c.emit_hi = c.next_out;
+  if (accept) {
+    const double t_new = t_start + dt;  // dopri5.py:116
+    c.t0 = t_start;
+    c.t1 = t_new;
+    c.emit_t0 = t_start;
+    c.emit_t1 = t_new;
+    c.emit_dt = dt;
+    c.emit_parity = c.parity;
+    c.parity ^= 1;  // y1 -> y0, k7 -> k1 (FSAL)
+    c.n_accept += 1;
+    // every requested time already covered by this step is emitted now (dopri5.py:85-92:
+    // the while loop is not entered again for them)
+    int hi = c.next_out;
+    while (hi < c.n_out && !(t_out[hi] > t_new)) ++hi;
+    if (hi > c.next_out) c.steps_this_interval = 0;
+    else c.steps_this_interval += 1;
+    c.emit_hi = hi;
+    c.next_out = hi;
+  } else {
+    c.t0 = t_start;  // rejected: (t0, t1) collapse onto the step start (dopri5.py:120)
+    c.n_reject += 1;
+    c.steps_this_interval += 1;
+  }
+  if (!c.forced) {
+    // _optimal_step_size, misc.py:160-170
+    double dt_next;
+    if (msr == 0.0f) {
+      dt_next = dt * c.ifactor;
+    } else {
+      const double dfac = (msr < 1.0f) ? 1.0 : c.dfactor;
+      const double root = (double)sqrtf(msr);
+      const double expo = (double)0.2f;  // torch.tensor(1/order) is fp32 before .to(float64)
+      double factor = fmin(pow(root, expo) / c.safety, 1.0 / dfac);
+      factor = fmax(1.0 / c.ifactor, factor);
+      if (msr != msr) factor = (double)msr;  // torch.min/max propagate NaN
+      dt_next = dt / factor;
+    }
+    c.dt = dt_next;
+  }
+  if (c.next_out >= c.n_out) {
+    c.done = 1;
+  } else {
+    if (!(c.t1 + c.dt > c.t1)) {  // dopri5.py:100
+      c.status = NDCN_E_DT_UNDERFLOW;
+      c.done = 1;
+    } else if (c.steps_this_interval >= c.max_num_steps) {  // dopri5.py:89
+      c.status = NDCN_E_MAX_STEPS;
+      c.done = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense output of the accepted step for every requested time inside it.
+// _interp_fit_dopri5 (dopri5.py:39-45) + _interp_fit (interp.py:5-35) +
+// _interp_evaluate (interp.py:38-65), fused per element; nothing but the outputs is stored.
+// ---------------------------------------------------------------------------------------
+struct EmitArgs {
+  Ctrl* ctrl;
+  const double* t_out;
+  PtrPair y0, y1, k0, k6;  // parity-selected by Ctrl::emit_parity
+  const float* k[5];       // k1..k5
+  float c_mid[7];          // fp32(DPS_C_MID)
+  float* out;              // [n_out, numel] or [numel] (terminal only)
+  int64_t numel;
+};
+
+template <int VW>
+__device__ __forceinline__ void emit_elem(const EmitArgs& a, const float* y0p, const float* y1p, const float* k0p,
+                                          const float* k6p, int64_t off, float dt, int lo, int hi, const float* xs_all,
+                                          int terminal_only, int n_out) {
+  float y0[VW], y1[VW], kk[7][VW];
+  ldv<VW>(y0p + off, y0);
+  ldv<VW>(y1p + off, y1);
+  ldv<VW>(k0p + off, kk[0]);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) ldv<VW>(a.k[j] + off, kk[j + 1]);
+  ldv<VW>(k6p + off, kk[6]);
+  float ca[VW], cb[VW], cc[VW], cd[VW];
+  const float m2dt = fmul(-2.f, dt), p2dt = fmul(2.f, dt), p5dt = fmul(5.f, dt), m3dt = fmul(-3.f, dt),
+              m4dt = fmul(-4.f, dt);
+#pragma unroll
+  for (int i = 0; i < VW; ++i) {
+    float acc = fmul(fmul(dt, a.c_mid[0]), kk[0][i]);
+#pragma unroll
+    for (int j = 1; j < 7; ++j) acc = fadd(acc, fmul(fmul(dt, a.c_mid[j]), kk[j][i]));
+    const float ymid = fadd(y0[i], acc);
+    const float f0 = kk[0][i], f1 = kk[6][i];
+    // a = -2dt f0 + 2dt f1 - 8 y0 - 8 y1 + 16 ymid
+    ca[i] = fadd(fadd(fadd(fadd(fmul(m2dt, f0), fmul(p2dt, f1)), fmul(-8.f, y0[i])), fmul(-8.f, y1[i])), fmul(16.f, ymid));
+    // b = 5dt f0 - 3dt f1 + 18 y0 + 14 y1 - 32 ymid
+    cb[i] = fadd(fadd(fadd(fadd(fmul(p5dt, f0), fmul(m3dt, f1)), fmul(18.f, y0[i])), fmul(14.f, y1[i])), fmul(-32.f, ymid));
+    // c = -4dt f0 + dt f1 - 11 y0 - 5 y1 + 16 ymid
+    cc[i] = fadd(fadd(fadd(fadd(fmul(m4dt, f0), fmul(dt, f1)), fmul(-11.f, y0[i])), fmul(-5.f, y1[i])), fmul(16.f, ymid));
+    cd[i] = fmul(dt, f0);
+  }
+  for (int j = lo; j < hi; ++j) {
+    if (terminal_only && j != n_out - 1) continue;
+    const float* xs = xs_all + (j - lo) * 4;  // x, x^2, x^3, x^4
+    float o[VW];
+#pragma unroll
+    for (int i = 0; i < VW; ++i)
+      o[i] = fadd(fadd(fadd(fadd(fmul(ca[i], xs[3]), fmul(cb[i], xs[2])), fmul(cc[i], xs[1])), fmul(cd[i], xs[0])),
+                  fmul(y0[i], 1.0f));
+    float* dst = terminal_only ? a.out : a.out + (int64_t)j * a.numel;
+    stv<VW>(dst + off, o);
+  }
+}
+
+constexpr int kEmitMaxPerLaunch = 32;
+
+__global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
+  const volatile Ctrl* ct = a.ctrl;
+  const int lo0 = ct->emit_lo, hi0 = ct->emit_hi;
+  if (lo0 >= hi0) return;
+  const int par = ct->emit_parity;
+  const int terminal_only = ct->terminal_only, n_out = ct->n_out;
+  if (terminal_only && hi0 != n_out) return;
+  const float t0 = (float)ct->emit_t0, t1 = (float)ct->emit_t1;  // interp.py:54-56
+  const float dt = (float)ct->emit_dt;                            // dopri5.py:41
+  const float* y0p = sel(a.y0, par);
+  const float* y1p = sel(a.y1, par);
+  const float* k0p = sel(a.k0, par);
+  const float* k6p = sel(a.k6, par);
+  __shared__ float xs[kEmitMaxPerLaunch * 4];
+  for (int lo = lo0; lo < hi0; lo += kEmitMaxPerLaunch) {
+    const int hi = min(hi0, lo + kEmitMaxPerLaunch);
+    __syncthreads();
+    if ((int)threadIdx.x < hi - lo) {
+      const float t = (float)a.t_out[lo + threadIdx.x];
+      const float x = fdiv(fsub(t, t0), fsub(t1, t0));
+      float p = x;
+      xs[threadIdx.x * 4 + 0] = p;
+      p = fmul(p, x); xs[threadIdx.x * 4 + 1] = p;
+      p = fmul(p, x); xs[threadIdx.x * 4 + 2] = p;
+      p = fmul(p, x); xs[threadIdx.x * 4 + 3] = p;
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+      const int64_t n4 = a.numel >> 2;
+      for (int64_t i = tid; i < n4; i += stride)
+        emit_elem<4>(a, y0p, y1p, k0p, k6p, i * 4, dt, lo, hi, xs, terminal_only, n_out);
+      for (int64_t i = (n4 << 2) + tid; i < a.numel; i += stride)
+        emit_elem<1>(a, y0p, y1p, k0p, k6p, i, dt, lo, hi, xs, terminal_only, n_out);
+    } else {
+      for (int64_t i = tid; i < a.numel; i += stride)
+        emit_elem<1>(a, y0p, y1p, k0p, k6p, i, dt, lo, hi, xs, terminal_only, n_out);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// _select_initial_step (misc.py:84-143), fp32, RMS norms, order = 4 for dopri5.
+// ---------------------------------------------------------------------------------------
+// partials[2*b+0] += sum (u/scale)^2, partials[2*b+1] += sum (v/scale)^2, scale = atol+|y0|*rtol
+// mode 0: u = y0, v = f0          (d0, d1)
+// mode 1: u = f1 - f0, v unused   (d2)
+__global__ void __launch_bounds__(kStageThreads) k_init_norms(const float* y0, const float* f0, const float* f1,
+                                                              int64_t numel, float rtol, float atol, int mode,
+                                                              double* partials) {
+  double s0 = 0.0, s1 = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const float y = y0[i];
+    const float scale = fadd(atol, fmul(fabsf(y), rtol));
+    if (mode == 0) {
+      const float u = fdiv(y, scale), v = fdiv(f0[i], scale);
+      s0 += (double)fmul(u, u);
+      s1 += (double)fmul(v, v);
+    } else {
+      const float u = fdiv(fsub(f1[i], f0[i]), scale);
+      s0 += (double)fmul(u, u);
+    }
+  }
+  __shared__ double r0[32], r1[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { r0[warp] = s0; r1[warp] = s1; }
+  __syncthreads();
+  if (warp == 0) {
+    double a = lane < (int)(blockDim.x >> 5) ? r0[lane] : 0.0;
+    double b = lane < (int)(blockDim.x >> 5) ? r1[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b; }
+  }
+}
+
+// phase 0: h0 from d0,d1.   phase 1: dt from d1,d2 and controller initialisation.
+// xchg (multi-GPU): the two sums are staged there for the host hook's all-reduce;
+// xchg_stage 0 = reduce+decide, 1 = reduce only, 2 = decide from xchg.
+__global__ void __launch_bounds__(kStageThreadsCtl) k_init_scalar(Ctrl* ctrl, const double* partials, int n_partials,
+                                                                  int phase, double t_first, double* xchg,
+                                                                  int xchg_stage) {
+  __shared__ double s_tmp[kStageThreadsCtl];
+  double sums[2] = {0.0, 0.0};
+  if (xchg_stage != 2) {
+    for (int q = 0; q < 2; ++q) {
+      double v = 0.0;
+      for (int i = threadIdx.x; i < n_partials; i += blockDim.x) v += partials[2 * i + q];
+      s_tmp[threadIdx.x] = v;
+      __syncthreads();
+      for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_tmp[threadIdx.x] += s_tmp[threadIdx.x + o];
+        __syncthreads();
+      }
+      sums[q] = s_tmp[0];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x != 0) return;
+  if (xchg_stage == 1) { xchg[0] = sums[0]; xchg[1] = sums[1]; return; }
+  if (xchg_stage == 2) { sums[0] = xchg[0]; sums[1] = xchg[1]; }
+  Ctrl& c = *ctrl;
+  const float rootn = (float)sqrt(c.numel_global);  // numel ** 0.5, a Python float -> fp32 divisor
+  if (phase == 0) {
+    const float d0 = fdiv((float)sqrt(sums[0]), rootn);
+    const float d1 = fdiv((float)sqrt(sums[1]), rootn);
+    c.d0 = d0;
+    c.d1 = d1;
+    c.h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : fmul(0.01f, fdiv(d0, d1));
+  } else {
+    const float h0 = c.h0, d1 = c.d1;
+    const float d2 = fdiv(fdiv((float)sqrt(sums[0]), rootn), h0);
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, fmul(h0, 1e-3f));
+    else h1 = powf(fdiv(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
+    const float h = fminf(fmul(100.f, h0), h1);
+    c.dt = (double)h;
+    c.first_step = (double)h;
+    c.t0 = c.t1 = t_first;
+    if (!(c.t1 + c.dt > c.t1)) { c.status = NDCN_E_DT_UNDERFLOW; c.done = 1; }
+  }
+}
+
+// error-ratio sum as a stand-alone op (C ABI ndcn_error_ratio_f32)
+__global__ void __launch_bounds__(kStageThreads) k_error_ratio(const float* err, const float* y0, const float* y1,
+                                                               int64_t numel, float rtol, float atol, double* partials) {
+  double s = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const float tol = fadd(atol, fmul(rtol, fmaxf(fabsf(y0[i]), fabsf(y1[i]))));
+    const float r = fdiv(err[i], tol);
+    s += (double)fmul(r, r);
+  }
+  __shared__ double red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) partials[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kStageThreadsCtl) k_sum_partials(const double* partials, int n, double* out) {
+  const double s = block_sum_partials(partials, n);
+  if (threadIdx.x == 0) *out = s;
+}
+
+// W [n][k] -> Wt [k][n]   (once per solve; H*H elements)
+__global__ void k_transpose(const float* __restrict__ W, float* __restrict__ Wt, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * H) {
+    const int n = i / H, k = i % H;
+    Wt[(size_t)k * H + n] = W[i];
+  }
+}
+
+}  // namespace ndcn

@@ -1,0 +1,144 @@
+"""``odeint(func, y0, t, ...)`` with the reference's signature and error behaviour
+(torchdiffeq/_impl/odeint.py:20-76, misc.py:173-195), dispatching to the fused CUDA solver.
+
+Dispatch
+  * ``func`` is recognised (our ``ODEFunc``; ``HeatDiffusion`` / ``GeneDynamics`` /
+    ``MutualDynamics`` -- ours or the reference scripts' own classes, duck-typed by class name
+    and attributes), no gradient is required, the state is one fp32 [N, d] tensor and the method
+    is one of euler | midpoint | rk4 | dopri5  ->  ``solver.odeint_fused`` (one C call).
+    CPU inputs are staged to the current CUDA device and the result is returned on the CPU
+    (the reference scripts always integrate their ground truth on CPU tensors,
+    heat_dynamics.py:207-209).
+  * otherwise (gradients needed, or an arbitrary callable) -> ``autograd_solver.solve`` on CUDA
+    tensors.
+  * no CUDA device / library not built -> RuntimeError.  Never a CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import autograd_solver, solver
+from .graph import CsrGraph, cached_graph, require_cuda
+from .solver import RhsSpec
+
+SOLVER_NAMES = ("explicit_adams", "fixed_adams", "adams", "tsit5", "dopri5", "euler", "midpoint", "rk4")
+FUSED_METHODS = ("euler", "midpoint", "rk4", "dopri5")
+
+
+def _is_number(v) -> bool:
+    return isinstance(v, (int, float)) and not isinstance(v, bool)
+
+
+def recognise(func, width: int, device: torch.device) -> Optional[Tuple[CsrGraph, RhsSpec]]:
+    """(graph, rhs) if ``func`` is one of the path's right-hand sides, else None."""
+    name = type(func).__name__
+    if name == "ODEFunc" and hasattr(func, "wt") and hasattr(func, "A"):
+        if getattr(func, "dropout", 0.0) and getattr(func, "training", False):
+            return None  # active dropout: RNG-dependent, not fusable
+        no_graph = bool(getattr(func, "no_graph", False))
+        no_control = bool(getattr(func, "no_control", False))
+        wt = func.wt
+        if int(wt.in_features) != width or int(wt.out_features) != width:
+            return None
+        graph = cached_graph(func, func.A, device)
+        W = wt.weight.to(device) if not no_control else None
+        b = wt.bias.to(device) if (not no_control and wt.bias is not None) else None
+        if not no_control and b is None:
+            b = torch.zeros(width, device=device)
+        return graph, RhsSpec.ndcn(width, W, b, no_graph=no_graph, no_control=no_control)
+    if name == "HeatDiffusion" and hasattr(func, "L") and _is_number(getattr(func, "k", None)):
+        # the module already stores -L (heat_dynamics.py:190)
+        return cached_graph(func, func.L, device), RhsSpec.heat(width, func.k)
+    if name == "GeneDynamics" and hasattr(func, "A") and all(_is_number(getattr(func, a, None)) for a in "bfh"):
+        return cached_graph(func, func.A, device), RhsSpec.gene(width, func.b, func.f, func.h)
+    if name == "MutualDynamics" and hasattr(func, "A") and all(_is_number(getattr(func, a, None)) for a in "bkcdeh"):
+        return cached_graph(func, func.A, device), RhsSpec.mutual(width, func.b, func.k, func.c, func.d, func.e, func.h)
+    return None
+
+
+def _needs_grad(func, y0: torch.Tensor) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if y0.requires_grad:
+        return True
+    params = getattr(func, "parameters", None)
+    if callable(params):
+        try:
+            return any(p.requires_grad for p in params())
+        except TypeError:
+            return False
+    return False
+
+
+def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, terminal_only: bool = False):
+    """Drop-in for ``torchdiffeq.odeint`` (vendored 2019 API, odeint.py:20).
+
+    ``terminal_only`` (keyword-only extension used by ``ODEBlock(terminal=True)``) returns just
+    ``y(t[-1])`` without materialising the ``[T, N, H]`` slab the reference builds and discards
+    (neural_dynamics.py:79).
+    """
+    tuple_input = False
+    if not torch.is_tensor(y0):
+        # misc.py:173-183
+        assert isinstance(y0, tuple), "y0 must be either a torch.Tensor or a tuple"
+        for y0_ in y0:
+            assert torch.is_tensor(y0_), "each element must be a torch.Tensor but received {}".format(type(y0_))
+        if len(y0) != 1:
+            raise NotImplementedError("ndcn_b200.odeint: tuple states with more than one tensor are outside the "
+                                      "accelerated path (only torchdiffeq's adjoint uses them)")
+        tuple_input = True
+        inner = func
+        func = lambda tt, yy: inner(tt, (yy,))[0]  # noqa: E731
+        y0 = y0[0]
+    if options is None:
+        options = {}
+    elif method is None:
+        raise ValueError("cannot supply `options` without specifying `method`")
+    if method is None:
+        method = "dopri5"
+    if method not in SOLVER_NAMES:
+        raise KeyError(method)  # SOLVERS[method] in the reference (odeint.py:71)
+    if method not in FUSED_METHODS:
+        raise NotImplementedError("ndcn_b200 implements euler | midpoint | rk4 | dopri5 (the methods on the "
+                                  "benchmarked path); %r is out of scope" % (method,))
+    if not torch.is_floating_point(y0):
+        raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y0.type()))
+    if not torch.is_floating_point(t):
+        raise TypeError("`t` must be a floating point Tensor but is a {}".format(t.type()))
+    if t.numel() > 1 and bool((t[1:] < t[:-1]).all()):
+        # decreasing times: integrate the mirrored system (misc.py:185-188)
+        base = func
+        t = -t
+        func = lambda tt, yy: -base(-tt, yy)  # noqa: E731
+    unknown = {k: v for k, v in options.items() if k not in ("max_num_steps",)}
+    max_num_steps = int(options.get("max_num_steps", 0) or 0)
+
+    out = None
+    fusable = (y0.dim() == 2 and y0.dtype == torch.float32 and not unknown and not _needs_grad(func, y0))
+    if fusable:
+        dev = require_cuda(y0.device if y0.is_cuda else None)
+        bound = recognise(func, int(y0.shape[1]), dev)
+        if bound is not None:
+            graph, spec = bound
+            if graph.n_rows != y0.shape[0]:
+                raise RuntimeError("size mismatch: operator is %dx%d, state has %d rows" %
+                                   (graph.n_rows, graph.n_cols, y0.shape[0]))
+            res = solver.odeint_fused(graph, spec, y0.detach().to(dev), t, method=method, rtol=float(rtol),
+                                      atol=float(atol), terminal_only=terminal_only, max_num_steps=max_num_steps)
+            out = res if y0.is_cuda else res.to(y0.device)
+    if out is None:
+        require_cuda(y0.device if y0.is_cuda else None)
+        kw = dict(max_num_steps=max_num_steps) if max_num_steps > 0 else {}
+        out = autograd_solver.solve(func, y0, t, float(rtol), float(atol), method, **kw)
+        if terminal_only:
+            out = out[-1]
+    return (out,) if tuple_input else out
+
+
+def odeint_adjoint(func, y0, t, rtol=1e-6, atol=1e-12, method=None, options=None):
+    """Signature of torchdiffeq/_impl/adjoint.py:105.  No script of the reference enables the
+    adjoint (SURVEY.md section 2, row "Adjoint backward"); gradients are obtained by
+    backpropagating through the solver instead of re-solving the augmented system."""
+    return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)

@@ -1,0 +1,215 @@
+"""Host side of the fused solve: tensor plumbing around ``ndcn_odeint_f32``.
+
+PyTorch is used for device memory (state, output slab, workspace) and the current stream;
+every arithmetic operation of the path happens inside libndcn_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _ffi
+from .graph import CsrGraph, require_cuda
+
+
+@dataclass
+class RhsSpec:
+    """Which right-hand side to evaluate (mirrors ``ndcn_rhs_desc_t``)."""
+
+    kind: int
+    H: int
+    flags: int = 0
+    W: Optional[torch.Tensor] = None  # [H, H] nn.Linear weight (y = x W^T + b)
+    b: Optional[torch.Tensor] = None  # [H]
+    p: Sequence[float] = field(default_factory=lambda: (0.0,) * 8)
+    callback: Optional[Callable] = None  # python callable (y_ptr, k_ptr, t_ptr) -> int
+
+    @staticmethod
+    def ndcn(H: int, W: Optional[torch.Tensor], b: Optional[torch.Tensor], no_graph=False, no_control=False,
+             relu=True) -> "RhsSpec":
+        flags = (_ffi.F_NO_GRAPH if no_graph else 0) | (_ffi.F_NO_CONTROL if no_control else 0) | \
+                (0 if relu else _ffi.F_NO_RELU)
+        return RhsSpec(_ffi.RHS_NDCN, H, flags, W, b)
+
+    @staticmethod
+    def heat(d: int, k: float = 1.0) -> "RhsSpec":
+        return RhsSpec(_ffi.RHS_HEAT, d, p=(float(k),) + (0.0,) * 7)
+
+    @staticmethod
+    def gene(d: int, b: float = 1.0, f: float = 1.0, h: float = 2.0) -> "RhsSpec":
+        return RhsSpec(_ffi.RHS_GENE, d, p=(float(b), float(f), float(h)) + (0.0,) * 5)
+
+    @staticmethod
+    def mutual(dim: int, b=0.1, k=5.0, c=1.0, d=5.0, e=0.9, h=0.1) -> "RhsSpec":
+        return RhsSpec(_ffi.RHS_MUTUAL, dim, p=(float(b), float(k), float(c), float(d), float(e), float(h), 0.0, 0.0))
+
+    def to_c(self, keep: list) -> _ffi.RhsDesc:
+        d = _ffi.RhsDesc()
+        d.kind, d.flags, d.H = self.kind, self.flags, self.H
+        if self.W is not None:
+            W = self.W.detach().to(torch.float32).contiguous()
+            keep.append(W)
+            d.W = W.data_ptr()
+        if self.b is not None:
+            b = self.b.detach().to(torch.float32).contiguous()
+            keep.append(b)
+            d.b = b.data_ptr()
+        for i, v in enumerate(self.p):
+            d.p[i] = v
+        if self.callback is not None:
+            cb = _ffi.RHS_CALLBACK(self.callback)
+            keep.append(cb)
+            d.callback = cb
+        return d
+
+
+@dataclass
+class SolveInfo:
+    """Counters of one solve (the reference keeps ``nfe`` only in comments, neural_dynamics.py:15)."""
+
+    nfe: int = 0
+    n_accepted: int = 0
+    n_rejected: int = 0
+    n_launches: int = 0
+    first_step: float = float("nan")
+    last_dt: float = float("nan")
+    t_final: float = float("nan")
+    status: int = 0
+
+
+last_solve_info: Optional[SolveInfo] = None
+
+_WORKSPACES: Dict[Tuple[str, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """One reusable byte buffer per device, grown on demand (training loops call odeint
+    thousands of times with the same shapes)."""
+    key = (str(device), 0)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _WORKSPACES.pop(key, None)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+_SOLVERS: Dict[tuple, tuple] = {}
+
+
+def release_workspaces() -> None:
+    for handle, _g in _SOLVERS.values():
+        _ffi.lib().ndcn_solver_destroy(handle)
+    _SOLVERS.clear()
+    _WORKSPACES.clear()
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def rhs_eval(graph: CsrGraph, spec: RhsSpec, x: torch.Tensor) -> torch.Tensor:
+    """One evaluation f(x) on the GPU (ODEFunc.forward / *Dynamics.forward)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+    x = x.contiguous()
+    if x.shape[0] != graph.n_cols or x.shape[1] != spec.H:
+        raise ValueError("state of shape %s does not match graph with %d nodes / width %d" %
+                         (tuple(x.shape), graph.n_cols, spec.H))
+    out = torch.empty((graph.n_rows, spec.H), dtype=torch.float32, device=x.device)
+    keep: list = []
+    desc = spec.to_c(keep)
+    with torch.cuda.device(x.device):
+        rc = _ffi.lib().ndcn_rhs_eval_f32(graph.handle, C.byref(desc), x.data_ptr(), out.data_ptr(),
+                                          current_stream_ptr(x.device))
+    _ffi.check(rc, "ndcn_rhs_eval_f32")
+    return out
+
+
+def spmm(graph: CsrGraph, x: torch.Tensor) -> torch.Tensor:
+    """Phi @ x (torch.sparse.mm / torch.mm at neural_dynamics.py:27-31)."""
+    return rhs_eval(graph, RhsSpec.ndcn(x.shape[1], None, None, no_control=True, relu=False), x)
+
+
+def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tensor, *, method: str = "dopri5",
+                 rtol: float = 1e-7, atol: float = 1e-9, terminal_only: bool = False,
+                 forced_dt: Optional[float] = None, max_num_steps: int = 0,
+                 exchange: Optional[Callable] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``torchdiffeq.odeint`` for a recognised RHS, entirely inside the CUDA library.
+
+    y0: [n_rows, H] fp32 CUDA.  t: 1-D float tensor (any device); the values are used as
+    given, promoted to float64 (callers that mirror ``ODEBlock`` round to fp32 first,
+    neural_dynamics.py:71).  Returns ``[len(t), n_rows, H]`` (or ``[n_rows, H]`` if
+    ``terminal_only``), and leaves counters in ``ndcn_b200.solver.last_solve_info``.
+    """
+    global last_solve_info
+    if method not in _ffi.METHODS:
+        raise ValueError("fused path covers %s, got %r" % (sorted(_ffi.METHODS), method))
+    dev = require_cuda(y0.device)
+    assert y0.is_cuda and y0.dtype == torch.float32 and y0.dim() == 2
+    if y0.shape[0] != graph.n_rows or y0.shape[1] != spec.H:
+        raise ValueError("y0 of shape %s does not match graph with %d rows / width %d" %
+                         (tuple(y0.shape), graph.n_rows, spec.H))
+    y0 = y0.contiguous()
+    if y0.data_ptr() % 16:
+        y0 = y0.clone()
+    t64 = t.detach().to("cpu", torch.float64).contiguous()
+    n_t = int(t64.numel())
+    if n_t < 1:
+        raise ValueError("t must hold at least one time")
+    if n_t > 1 and not bool((t64[1:] > t64[:-1]).all()):
+        # misc.py:59-60
+        raise AssertionError("t must be strictly increasing or decrasing")
+    lib = _ffi.lib()
+    method_id = _ffi.METHODS[method]
+    keep: list = []
+    desc = spec.to_c(keep)
+    shape = (graph.n_rows, spec.H) if terminal_only else (n_t, graph.n_rows, spec.H)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == shape and out.is_cuda and out.is_contiguous() and out.dtype == torch.float32
+    opts = _ffi.SolveOpts()
+    opts.method = method_id
+    opts.flags = (_ffi.O_TERMINAL_ONLY if terminal_only else 0) | (_ffi.O_FORCED_DT if forced_dt is not None else 0)
+    opts.rtol, opts.atol = float(rtol), float(atol)
+    opts.forced_dt = float(forced_dt) if forced_dt is not None else 0.0
+    opts.max_num_steps = int(max_num_steps)
+    if exchange is not None:
+        cb = _ffi.EXCHANGE_CALLBACK(exchange)
+        keep.append(cb)
+        opts.exchange = cb
+    stats = _ffi.SolveStats()
+    with torch.cuda.device(dev):
+        nbytes = lib.ndcn_solver_workspace_bytes(graph.n_rows, graph.n_cols, spec.H, method_id)
+        ws = _workspace(dev, int(nbytes))
+        # solver handles own pinned/ctrl scratch (cudaMallocHost is slow): keep a few alive,
+        # keyed on everything the handle captured by pointer
+        key = (id(graph), spec.kind, spec.flags, spec.H, method_id, desc.W, desc.b, tuple(spec.p),
+               ws.data_ptr(), spec.callback is not None)
+        entry = _SOLVERS.get(key)
+        if entry is None or spec.callback is not None:
+            handle = C.c_void_p()
+            _ffi.check(lib.ndcn_solver_create(graph.handle, C.byref(desc), method_id, ws.data_ptr(), ws.numel(),
+                                              C.byref(handle)), "ndcn_solver_create")
+            if len(_SOLVERS) >= 8:
+                _, (old, _g) = _SOLVERS.popitem()
+                lib.ndcn_solver_destroy(old)
+            if spec.callback is None:
+                _SOLVERS[key] = (handle, graph)
+        else:
+            handle = entry[0]
+        try:
+            t_ptr = C.cast(t64.data_ptr(), _ffi.c_double_p)
+            rc = lib.ndcn_odeint_f32(handle, y0.data_ptr(), t_ptr, n_t, out.data_ptr(), C.byref(opts),
+                                     C.byref(stats), current_stream_ptr(dev))
+        finally:
+            if spec.callback is not None:
+                lib.ndcn_solver_destroy(handle)
+    last_solve_info = SolveInfo(stats.nfe, stats.n_accepted, stats.n_rejected, stats.n_launches, stats.first_step,
+                                stats.last_dt, stats.t_final, stats.status)
+    _ffi.check(rc, "ndcn_odeint_f32")
+    return out

@@ -1,0 +1,173 @@
+"""GPU: whole solves through the C ABI (ndcn_odeint_f32) vs the oracle and the reference goldens.
+Adaptive runs at the NDCN tolerances must also reproduce (nfe, accepted, rejected)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import csr_to_coo, csr_to_dense
+from oracle import ndcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 1e-6
+
+
+def _info():
+    from ndcn_b200 import solver
+    return solver.last_solve_info
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4", "dopri5"])
+def test_ndcn_grid_golden(golden, method):
+    import ndcn_b200 as nb
+    g = golden("ndcn_grid400")
+    OM = csr_to_dense(g, "OM")
+    W = torch.from_numpy(g["sd_neural_dynamic_layer__odefunc__wt__weight"]).cuda()
+    b = torch.from_numpy(g["sd_neural_dynamic_layer__odefunc__wt__bias"]).cuda()
+    h0, t = torch.from_numpy(g["h0"]).cuda(), torch.from_numpy(g["t"])
+    graph = nb.CsrGraph.from_tensor(OM, torch.device("cuda"))
+    hv = nb.odeint_fused(graph, nb.RhsSpec.ndcn(20, W, b), h0, t.float(), method=method, rtol=.01, atol=.001)
+    torch.testing.assert_close(hv[::10].cpu(), torch.from_numpy(g["hv_every10_" + method]), rtol=RTOL, atol=2e-6)
+    st = g["stats_" + method].tolist()
+    i = _info()
+    assert [i.nfe, i.n_accepted, i.n_rejected] == st
+    # terminal-only returns the last slice without the slab
+    yT = nb.odeint_fused(graph, nb.RhsSpec.ndcn(20, W, b), h0, t.float(), method=method, rtol=.01, atol=.001,
+                         terminal_only=True)
+    torch.testing.assert_close(yT, hv[-1], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("key", ["heat", "gene", "mutual"])
+def test_truth_dynamics_golden(golden, key):
+    """default tolerances (1e-7/1e-9): fp32 round-off decides individual steps, so compare the
+    solution, not the step sequence"""
+    import ndcn_b200 as nb
+    g = golden("truth_" + key)
+    A, L = csr_to_dense(g, "A"), csr_to_dense(g, "L")
+    op = -L if key == "heat" else A
+    spec = {"heat": nb.RhsSpec.heat(1, 1), "gene": nb.RhsSpec.gene(1, 1, 1, 2), "mutual": nb.RhsSpec.mutual(1)}[key]
+    graph = nb.CsrGraph.from_tensor(op, torch.device("cuda"))
+    x0, t = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["t"])
+    sol = nb.odeint_fused(graph, spec, x0, t, method="dopri5")
+    torch.testing.assert_close(sol.cpu(), torch.from_numpy(g["sol_dense"]), rtol=1e-4, atol=1e-4)
+    i = _info()
+    assert i.status == 0 and abs(i.nfe - int(g["nfe"])) < 0.2 * int(g["nfe"])
+    if key == "heat":
+        s = sol.double().sum(dim=(1, 2))
+        assert float((s - s[0]).abs().max()) < 1e-3 * float(s[0])
+
+
+def test_cora_block_golden(golden):
+    import ndcn_b200 as nb
+    g = golden("cora_block")
+    t = torch.linspace(0, 1.2, 16).float()
+    for H in (32, 256):
+        x = torch.from_numpy(np.tanh(np.random.RandomState(11).standard_normal((2708, H))).astype(np.float32)).cuda()
+        for tag in ("a05", "a00"):
+            graph = nb.CsrGraph.from_tensor(csr_to_coo(g, "adj_" + tag), torch.device("cuda"))
+            for ctl in ("ctl", "noctl"):
+                key = "%s_h%d_%s" % (tag, H, ctl)
+                W, b = torch.from_numpy(g["W_" + key]).cuda(), torch.from_numpy(g["b_" + key]).cuda()
+                spec = nb.RhsSpec.ndcn(H, W, b, no_control=(ctl == "noctl"))
+                yT = nb.odeint_fused(graph, spec, x, t, method="dopri5", rtol=.1, atol=.1, terminal_only=True).cpu()
+                ref = torch.from_numpy(g["yT_" + key])
+                torch.testing.assert_close(yT if H == 32 else yT[::8], ref, rtol=RTOL, atol=2e-6)
+                i = _info()
+                assert [i.nfe, i.n_accepted, i.n_rejected] == g["stats_" + key].tolist(), key
+
+
+def test_powerlaw_h256_golden(golden):
+    import ndcn_b200 as nb
+    g = golden("powerlaw2048_h256")
+    graph = nb.CsrGraph.from_tensor(csr_to_coo(g, "Phi"), torch.device("cuda"))
+    W, b = torch.from_numpy(g["W"]).cuda(), torch.from_numpy(g["b"]).cuda()
+    x = torch.from_numpy(np.random.RandomState(5).standard_normal((2048, 256)).astype(np.float32)).cuda()
+    for method, kw in (("rk4", {}), ("dopri5", dict(rtol=.01, atol=.001))):
+        y = nb.odeint_fused(graph, nb.RhsSpec.ndcn(256, W, b), x, torch.from_numpy(g["t_" + method]), method=method, **kw)
+        torch.testing.assert_close(y[-1][::4].cpu(), torch.from_numpy(g["y_" + method]), rtol=RTOL, atol=1e-5)
+        i = _info()
+        assert [i.nfe, i.n_accepted, i.n_rejected] == g["stats_" + method].tolist()
+
+
+@pytest.mark.parametrize("method", ["euler", "rk4", "dopri5"])
+def test_irregular_grid_vs_oracle(method):
+    """irregularly sampled output times (heat_dynamics.py:129-147), several outputs per step and
+    several steps per output"""
+    import ndcn_b200 as nb
+    n, H = 500, 64
+    rs = np.random.RandomState(2)
+    r = rs.randint(0, n, 2000); c = rs.randint(0, n, 2000)
+    k = r != c
+    Phi = O.normalized_laplacian_coo(np.concatenate([r[k], c[k]]), np.concatenate([c[k], r[k]]), n)
+    torch.manual_seed(4)
+    lin = torch.nn.Linear(H, H)
+    W, b = lin.weight.detach(), lin.bias.detach()
+    x = torch.randn(n, H)
+    t = torch.sort(torch.rand(23) * 3.0)[0]
+    t[0] = 0.0
+    t[5] = t[4] + 1e-4  # two outputs almost on top of each other
+    st = O.SolveStats()
+    ref = O.odeint(lambda tt, xx: O.rhs_ndcn(Phi, W, b, xx), x, t, rtol=1e-3, atol=1e-4, method=method, stats=st)
+    graph = nb.CsrGraph.from_tensor(Phi, torch.device("cuda"))
+    out = nb.odeint_fused(graph, nb.RhsSpec.ndcn(H, W.cuda(), b.cuda()), x.cuda(), t, method=method, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(out.cpu(), ref, rtol=RTOL, atol=1e-5)
+    i = _info()
+    assert [i.nfe, i.n_accepted, i.n_rejected] == [st.nfe, st.n_accepted, st.n_rejected]
+
+
+def test_rejected_steps_are_reproduced():
+    """a stiff-ish start forces rejections; accept/reject sequence must match the oracle"""
+    import ndcn_b200 as nb
+    n, H = 300, 32
+    torch.manual_seed(7)
+    A = (torch.rand(n, n) < 0.05).float() * 3.0
+    W, b = torch.randn(H, H) * 0.8, torch.randn(H) * 0.1
+    x = torch.randn(n, H) * 4
+    t = torch.tensor([0.0, 0.5, 2.0])
+    st = O.SolveStats()
+    ref = O.odeint(lambda tt, xx: O.rhs_ndcn(A, W, b, xx), x, t, rtol=1e-2, atol=1e-3, method="dopri5", stats=st)
+    graph = nb.CsrGraph.from_tensor(A, torch.device("cuda"))
+    out = nb.odeint_fused(graph, nb.RhsSpec.ndcn(H, W.cuda(), b.cuda()), x.cuda(), t, rtol=1e-2, atol=1e-3)
+    i = _info()
+    assert st.n_rejected > 0
+    assert [i.nfe, i.n_accepted, i.n_rejected] == [st.nfe, st.n_accepted, st.n_rejected]
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
+
+
+def test_forced_dt_steps_vs_oracle():
+    """the bench workload: S forced dopri5 steps of size T/S with the error estimate computed"""
+    import ndcn_b200 as nb
+    n, H = 1000, 256
+    rs = np.random.RandomState(9)
+    r = rs.randint(0, n, 5000); c = rs.randint(0, n, 5000)
+    k = r != c
+    Phi = O.normalized_laplacian_coo(np.concatenate([r[k], c[k]]), np.concatenate([c[k], r[k]]), n)
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(H, H)
+    W, b = lin.weight.detach() * 0.5, lin.bias.detach()
+    x = torch.randn(n, H)
+    t = torch.tensor([0.0, 1.0])
+    st = O.SolveStats()
+    ref = O.odeint(lambda tt, xx: O.rhs_ndcn(Phi, W, b, xx), x, t, method="dopri5", stats=st, forced_dt=0.1)
+    graph = nb.CsrGraph.from_tensor(Phi, torch.device("cuda"))
+    out = nb.odeint_fused(graph, nb.RhsSpec.ndcn(H, W.cuda(), b.cuda()), x.cuda(), t, method="dopri5", forced_dt=0.1,
+                          terminal_only=True)
+    i = _info()
+    assert i.n_accepted == st.n_accepted == 10 and i.n_rejected == 0 and i.nfe == st.nfe
+    torch.testing.assert_close(out.cpu(), ref[-1], rtol=RTOL, atol=1e-5)
+
+
+def test_error_behaviour():
+    import ndcn_b200 as nb
+    A = torch.eye(4)
+    graph = nb.CsrGraph.from_tensor(A, torch.device("cuda"))
+    x = torch.ones(4, 1).cuda()
+    with pytest.raises(AssertionError):  # misc.py:59-60
+        nb.odeint_fused(graph, nb.RhsSpec.heat(1, 1.0), x, torch.tensor([0.0, 1.0, 0.5]))
+    with pytest.raises(AssertionError, match="non-finite"):  # dopri5.py:102
+        nb.odeint_fused(graph, nb.RhsSpec.heat(1, 1.0), x * float("inf"), torch.tensor([0.0, 1.0]))
+    with pytest.raises(ValueError):
+        nb.odeint_fused(graph, nb.RhsSpec.heat(1, 1.0), x, torch.tensor([0.0, 1.0]), method="tsit5")
+    # exploding dynamics: x' = 50 x^2-like growth through the mutualistic term ends in a non-finite state
+    with pytest.raises(AssertionError):
+        big = nb.CsrGraph.from_tensor(torch.ones(4, 4) * 1e6, torch.device("cuda"))
+        nb.odeint_fused(big, nb.RhsSpec.heat(1, 1e30), x, torch.tensor([0.0, 1e6]), rtol=1e-1, atol=1e-1)

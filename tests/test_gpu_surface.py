@@ -1,0 +1,143 @@
+"""GPU: the reference-facing Python surface (ODEFunc / ODEBlock / ODEBlock2 / NDCN / odeint, and the
+``neural_dynamics`` / ``torchdiffeq`` shim modules) against the reference outputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, csr_to_coo, csr_to_dense
+from oracle import ndcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 1e-6
+
+
+def _load_ndcn(g, OM, method, device):
+    import ndcn_b200 as nb
+    m = nb.NDCN(1, 20, OM, 1, rtol=.01, atol=.001, method=method)
+    sd = {k[3:].replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")}
+    assert sorted(sd) == sorted(m.state_dict().keys())  # same state_dict keys as the reference
+    m.load_state_dict(sd)
+    return m.to(device)
+
+
+@pytest.mark.parametrize("method", ["euler", "rk4", "dopri5"])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_ndcn_forward_golden(golden, method, sparse):
+    g = golden("ndcn_grid400")
+    OM = csr_to_coo(g, "OM") if sparse else csr_to_dense(g, "OM")
+    m = _load_ndcn(g, OM.cuda(), method, "cuda")
+    x0, t = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    with torch.no_grad():
+        y = m(t, x0)
+    ref = g["y_sparse_" + method] if sparse else g["y_" + method]
+    torch.testing.assert_close(y.cpu(), torch.from_numpy(ref), rtol=RTOL, atol=1e-5)
+
+
+def test_cpu_inputs_are_staged_and_returned_on_cpu(golden):
+    """ground-truth solves in the scripts run on CPU tensors (heat_dynamics.py:207-209)"""
+    import ndcn_b200 as nb
+    g = golden("truth_heat")
+    L = csr_to_dense(g, "L")
+    x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])
+    with torch.no_grad():
+        sol = nb.odeint(nb.HeatDiffusion(L, 1), x0, t, method="dopri5")
+    assert sol.device.type == "cpu" and sol.shape == (100, 400, 1)
+    torch.testing.assert_close(sol, torch.from_numpy(g["sol_dense"]), rtol=1e-4, atol=1e-4)
+
+
+def test_duck_typed_script_classes(golden):
+    """the scripts define HeatDiffusion/GeneDynamics/MutualDynamics themselves; odeint recognises
+    foreign classes by name + attributes"""
+    import ndcn_b200 as nb
+
+    class GeneDynamics(torch.nn.Module):  # same shape as gene_dynamics.py:186-205
+        def __init__(self, A, b, f=1, h=2):
+            super().__init__()
+            self.A, self.b, self.f, self.h = A, b, f, h
+
+        def forward(self, t, x):
+            raise AssertionError("the fused path must not call back into Python")
+
+    g = golden("truth_gene")
+    A = csr_to_dense(g, "A")
+    with torch.no_grad():
+        sol = nb.odeint(GeneDynamics(A, 1), torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), method="dopri5")
+    torch.testing.assert_close(sol, torch.from_numpy(g["sol_dense"]), rtol=1e-4, atol=1e-4)
+
+
+def test_odeblock2_terminal_cora(golden):
+    import ndcn_b200 as nb
+    g = golden("cora_block")
+    adj = csr_to_coo(g, "adj_a00").cuda()
+    key = "a00_h32_noctl"
+    fn = nb.ODEFunc(32, adj, dropout=0.0, no_control=True)
+    blk = nb.ODEBlock2(fn, torch.linspace(0, 1.2, 16).float(), rtol=.1, atol=.1, method="dopri5", terminal=True).cuda()
+    x = torch.from_numpy(np.tanh(np.random.RandomState(11).standard_normal((2708, 32))).astype(np.float32)).cuda()
+    blk.eval()
+    with torch.no_grad():
+        y = blk(x)
+    torch.testing.assert_close(y.cpu(), torch.from_numpy(g["yT_" + key]), rtol=RTOL, atol=2e-6)
+
+
+def test_training_step_gradients_match_cpu_autograd(golden):
+    """gradients through the solver (dgnn.py:204, heat_dynamics.py:333): differentiable path on the
+    GPU (our SpMM kernel forward/backward) vs plain CPU autograd through the oracle"""
+    import ndcn_b200 as nb
+    g = golden("ndcn_grid400")
+    OM = csr_to_dense(g, "OM")
+    x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])[:12]
+    for method in ("euler", "dopri5"):
+        m = _load_ndcn(g, OM.cuda(), method, "cuda")
+        y = m(t.cuda(), x0.cuda())
+        loss = y.abs().mean()
+        loss.backward()
+        # CPU oracle with autograd
+        W = torch.from_numpy(g["sd_neural_dynamic_layer__odefunc__wt__weight"]).requires_grad_()
+        b = torch.from_numpy(g["sd_neural_dynamic_layer__odefunc__wt__bias"]).requires_grad_()
+        enc = torch.nn.Sequential(torch.nn.Linear(1, 20), torch.nn.Tanh(), torch.nn.Linear(20, 20))
+        enc.load_state_dict({k[len("sd_input_layer__"):].replace("__", "."): torch.from_numpy(v)
+                             for k, v in g.items() if k.startswith("sd_input_layer")})
+        Wo, bo = torch.from_numpy(g["sd_output_layer__weight"]), torch.from_numpy(g["sd_output_layer__bias"])
+        hv = O.odeint(lambda tt, x: O.rhs_ndcn(OM, W, b, x), enc(x0), t.float(), rtol=.01, atol=.001, method=method)
+        ref_loss = torch.nn.functional.linear(hv, Wo, bo).abs().mean()
+        ref_loss.backward()
+        torch.testing.assert_close(loss.detach().cpu(), ref_loss.detach(), rtol=1e-4, atol=1e-6)
+        gw = m.neural_dynamic_layer.odefunc.wt.weight.grad.cpu()
+        torch.testing.assert_close(gw, W.grad, rtol=2e-3, atol=1e-6)
+
+
+def test_shim_modules_resolve_like_the_reference():
+    from ndcn_b200 import run
+    shim_dir = os.path.join(ROOT, "ndcn_b200", "shims")
+    saved = list(sys.path), dict(sys.modules)
+    try:
+        run.install(shim_dir)
+        import neural_dynamics
+        import torchdiffeq as ode
+        assert neural_dynamics.__file__.startswith(shim_dir) and ode.__file__.startswith(shim_dir)
+        for name in ("ODEFunc", "ODEBlock", "ODEBlock2", "NDCN", "torch", "nn", "F", "ode", "np"):
+            assert hasattr(neural_dynamics, name), name
+        assert callable(ode.odeint) and callable(ode.odeint_adjoint)
+        A = torch.eye(6).cuda()
+        fn = neural_dynamics.ODEFunc(4, A).cuda()
+        with torch.no_grad():
+            out = ode.odeint(fn, torch.ones(6, 4).cuda(), torch.tensor([0.0, 0.5, 1.0]), rtol=.01, atol=.001)
+        assert out.shape == (3, 6, 4) and out.is_cuda
+    finally:
+        sys.path[:] = saved[0]
+        for k in list(sys.modules):
+            if k not in saved[1]:
+                del sys.modules[k]
+
+
+def test_generic_callable_runs_on_gpu():
+    import ndcn_b200 as nb
+    y0 = torch.tensor([[1.0, 0.0]]).cuda()
+    M = torch.tensor([[0.0, 1.0], [-1.0, 0.0]]).cuda()
+    t = torch.linspace(0, 1, 5)
+    out = nb.odeint(lambda tt, y: y @ M, y0, t, rtol=1e-6, atol=1e-8, method="dopri5")
+    ref = O.odeint(lambda tt, y: y @ M.cpu(), y0.cpu(), t, rtol=1e-6, atol=1e-8, method="dopri5")
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-6)

@@ -1,0 +1,88 @@
+"""CPU: host-side logic that needs no GPU -- argument validation with the reference's exception
+types, module surface, loud failure without CUDA."""
+import inspect
+
+import pytest
+import torch
+
+import ndcn_b200 as nb
+from ndcn_b200 import _ffi
+
+
+def test_surface_signatures_match_reference():
+    assert list(inspect.signature(nb.ODEFunc.__init__).parameters) == \
+        ["self", "hidden_size", "A", "dropout", "no_graph", "no_control"]
+    assert list(inspect.signature(nb.ODEBlock.__init__).parameters) == \
+        ["self", "odefunc", "rtol", "atol", "method", "adjoint", "terminal"]
+    assert list(inspect.signature(nb.ODEBlock2.__init__).parameters) == \
+        ["self", "odefunc", "vt", "rtol", "atol", "method", "adjoint", "terminal"]
+    assert list(inspect.signature(nb.NDCN.__init__).parameters) == \
+        ["self", "input_size", "hidden_size", "A", "num_classes", "dropout", "no_embed", "no_graph", "no_control",
+         "rtol", "atol", "method"]
+    p = inspect.signature(nb.odeint).parameters
+    assert list(p)[:7] == ["func", "y0", "t", "rtol", "atol", "method", "options"]
+    assert p["rtol"].default == 1e-7 and p["atol"].default == 1e-9 and p["method"].default is None
+    pa = inspect.signature(nb.odeint_adjoint).parameters
+    assert pa["rtol"].default == 1e-6 and pa["atol"].default == 1e-12
+
+
+def test_state_dict_keys():
+    m = nb.NDCN(1, 20, torch.eye(4), 1)
+    assert sorted(m.state_dict()) == sorted([
+        "input_layer.0.weight", "input_layer.0.bias", "input_layer.2.weight", "input_layer.2.bias",
+        "neural_dynamic_layer.odefunc.wt.weight", "neural_dynamic_layer.odefunc.wt.bias",
+        "output_layer.weight", "output_layer.bias"])
+    assert not any(k.endswith(".A") for k in m.state_dict())  # A is a plain attribute (neural_dynamics.py:14)
+
+
+def test_odeint_argument_errors_match_reference():
+    f = lambda t, y: y  # noqa: E731
+    y0, t = torch.ones(2, 2), torch.tensor([0.0, 1.0])
+    with pytest.raises(ValueError):  # odeint.py:65-66
+        nb.odeint(f, y0, t, options={"x": 1})
+    with pytest.raises(KeyError):
+        nb.odeint(f, y0, t, method="nope")
+    with pytest.raises(TypeError):  # misc.py:190-193
+        nb.odeint(f, torch.ones(2, 2, dtype=torch.int64), t)
+    with pytest.raises(TypeError):
+        nb.odeint(f, y0, torch.tensor([0, 1]))
+    with pytest.raises(AssertionError):  # misc.py:180
+        nb.odeint(f, [y0], t)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    """without a CUDA device the hot path raises; it never computes on the CPU"""
+    L = torch.eye(4)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        nb.odeint(nb.HeatDiffusion(L, 1), torch.ones(4, 1), torch.tensor([0.0, 1.0]))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        nb.ODEFunc(4, L)(None, torch.ones(4, 4))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        nb.odeint(lambda t, y: y, torch.ones(2, 2), torch.tensor([0.0, 1.0]))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        nb.CsrGraph.from_tensor(L)
+
+
+def test_status_codes_map_to_reference_exceptions():
+    with pytest.raises(AssertionError, match="non-finite"):
+        _ffi.check(_ffi.E_NONFINITE)
+    with pytest.raises(AssertionError, match="underflow in dt"):
+        _ffi.check(_ffi.E_DT_UNDERFLOW)
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        _ffi.check(_ffi.E_MAX_STEPS)
+    with pytest.raises(ValueError):
+        _ffi.check(_ffi.E_ARG)
+    with pytest.raises(RuntimeError):
+        _ffi.check(700)
+    _ffi.check(0)
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.dirname(os.path.abspath(nb.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
