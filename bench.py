@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- node-state-updates/s of the NDCN ODE hot path on B200 (BASELINE.json metric).
+
+Workload (``config.workload``): the north-star configuration -- a 1M-node power-law graph
+(preferential attachment, m=5), Phi = I - D^-1/2 A D^-1/2 as fp32 CSR, hidden width 256,
+``relu((Phi X) W^T + b)`` integrated by dopri5 with a forced step dt = T/100 = 0.05 (error
+estimate computed every step, every step accepted: SURVEY.md section 8(d) "S dopri5 steps").
+One "step" = one dopri5 step over the whole state = 6 RHS evaluations + the stage algebra +
+the error norm.  ``value`` = N*H*steps / seconds with the state resident in HBM; ``e2e`` = the
+same solve through the public ``ndcn_b200.odeint(ODEFunc, y0, t)`` call with y0 in pinned HOST
+memory and the result returned to the host (H2D + D2H inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      the reference's CPU path (oracle port)
+
+N > 1: launched by torch.distributed.run, one rank per GPU; the graph is partitioned 1-D by
+node rows, halo rows are exchanged with NCCL before every RHS evaluation ("strong" scaling:
+the 1M-node problem is fixed).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "node-state-updates/sec (nodes x hidden x steps / s)"
+UNIT = "updates/s"
+T_TOTAL, STEPS_TOTAL = 5.0, 100  # north star: T=5, 100 dopri5 steps  ->  dt = 0.05
+DT = T_TOTAL / STEPS_TOTAL
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--nodes", type=int, default=1_000_000)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--graph", choices=["power_law", "er", "grid"], default="power_law")
+    ap.add_argument("--layout", choices=["generation", "degree"], default="generation")
+    ap.add_argument("--method", choices=["dopri5", "rk4", "euler"], default="dopri5")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds for the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------
+def build_operator(args, n):
+    from ndcn_b200 import workloads as wl
+
+    if args.graph == "power_law":
+        a = wl.power_law_adjacency(n, 5, seed=0)
+    elif args.graph == "er":
+        a = wl.erdos_renyi_adjacency(n, 10.0, seed=0)
+    else:
+        side = int(round(n ** 0.5))
+        a = wl.grid_adjacency(side)
+    if args.layout == "degree":
+        a, _ = wl.reorder_by_degree(a)
+    return wl.graph_operator(a, "norm_lap")
+
+
+def make_weights(H):
+    """nn.Linear(H, H) default init under seed 0, halved so that the state stays finite over T=5."""
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(H, H)
+    return (lin.weight.detach() * 0.5).contiguous(), lin.bias.detach().contiguous()
+
+
+def make_state(n, H, pin):
+    g = torch.Generator().manual_seed(0)
+    x = torch.empty((n, H), dtype=torch.float32, pin_memory=pin)
+    x.normal_(generator=g)
+    return x
+
+
+def bytes_rhs(n, nnz, H):
+    """algorithmic bytes of one RHS evaluation."""
+    return 2 * 4 * n * H + 8 * nnz + 4 * (n + 1) + 4 * H * H + 4 * H
+
+
+RHS_PER_STEP = {"dopri5": 6, "rk4": 4, "euler": 1}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                mx = float(parts[1])
+                if t0 <= ts <= t1 + 0.2:
+                    sm.append(float(parts[0]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         parts[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port; bit-identical to the reference on the same torch build,
+# tests/test_oracle_pinning.py) on a bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, budget_s):
+    """Times `steps` forced-dt steps of the reference algorithm on the host cores, on a graph of the
+    same family whose size is chosen so that warmup+steps fit in ~budget_s seconds."""
+    from ndcn_b200 import workloads as wl
+    from oracle import ndcn_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H = args.hidden
+    W, b = make_weights(H)
+    per_step = RHS_PER_STEP[args.method]
+
+    def setup(n):
+        a = wl.power_law_adjacency(n, 5, seed=0) if args.graph == "power_law" else \
+            (wl.erdos_renyi_adjacency(n, 10.0, seed=0) if args.graph == "er" else wl.grid_adjacency(int(round(n ** .5))))
+        phi = wl.to_reference_coo(wl.graph_operator(a, "norm_lap"))
+        return phi, make_state(phi.shape[0], H, False)
+
+    # calibrate on a small graph: seconds per (node * RHS evaluation)
+    n_cal = min(args.nodes, 32768)
+    phi, x = setup(n_cal)
+    with torch.no_grad():
+        O.rhs_ndcn(phi, W, b, x)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            O.rhs_ndcn(phi, W, b, x)
+        per_node_eval = (time.perf_counter() - t0) / 2 / n_cal
+    # a step costs ~ per_step RHS + ~as much again in solver algebra
+    est_per_node_step = per_node_eval * per_step * 2.0
+    n = int(budget_s / max(est_per_node_step * (steps + warmup), 1e-12))
+    n = max(4096, min(args.nodes, n))
+    if n != n_cal:
+        phi, x = setup(n)
+    n = phi.shape[0]
+
+    def run(k):
+        t = torch.tensor([0.0, DT * (k - 0.5)], dtype=torch.float64)  # inside the k-th step: exactly k steps
+        func = lambda tt, xx: O.rhs_ndcn(phi, W, b, xx)  # noqa: E731
+        with torch.no_grad():
+            if args.method == "dopri5":
+                return O.odeint(func, x, t, method="dopri5", forced_dt=DT)
+            return O.odeint(func, x, torch.linspace(0, DT * k, k + 1), method=args.method)
+
+    if warmup > 0:
+        run(warmup)
+    t0 = time.perf_counter()
+    run(steps)
+    dt = time.perf_counter() - t0
+    value = n * H * steps / dt
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d-node %s graph (same generator), H=%d, %d forced-dt %s steps after %d warm-up, "
+                      "torch %s CPU, reference algorithm via oracle port (COO sparse.mm + Linear + per-op solver algebra)"
+                      % (n, args.graph, H, steps, args.method, warmup, torch.__version__),
+            "seconds": dt, "ms_per_step": 1e3 * dt / steps, "nodes": n}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    budget = 120.0
+    res = cpu_reference_run(args, args.steps, args.warmup, budget)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.nodes, None),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n, nnz):
+    return {
+        "workload": "%s graph %d nodes (m=5 preferential attachment, %s order), Phi=norm. Laplacian CSR%s, hidden=%d, "
+                    "%s forced dt=%.3g (T=5 / 100 steps), one step = %d RHS evals + stage algebra + error norm"
+                    % (args.graph, n, args.layout, "" if nnz is None else " nnz=%d" % nnz, args.hidden, args.method, DT,
+                       RHS_PER_STEP[args.method]),
+        "nodes": n, "hidden": args.hidden, "method": args.method, "dt": DT,
+        "l2_policy": "inputs larger than L2 (state %.0f MB x >=11 buffers vs 126 MB L2), no flush" %
+                     (n * args.hidden * 4 / 1e6),
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def main_ours(args):
+    import ndcn_b200 as nb
+    from ndcn_b200 import _ffi, solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa
+        dist.init_process_group("nccl", device_id=dev)
+    _ffi.lib()  # fail loudly if the CUDA library is missing
+
+    n, H = args.nodes, args.hidden
+    phi = build_operator(args, n)
+    n = phi.shape[0]
+    nnz = int(phi.nnz)
+    W, b = make_weights(H)
+    W, b = W.to(dev), b.to(dev)
+    spec = nb.RhsSpec.ndcn(H, W, b)
+    x0_host = make_state(n, H, pin=True)
+
+    if world == 1:
+        graph = nb.CsrGraph.from_scipy(phi, dev)
+        exchange = None
+        x0 = x0_host.to(dev)
+        part = None
+    else:
+        from ndcn_b200 import partition
+        part = partition.RowPartition.build(phi, world, rank, dev, H)
+        graph = part.graph
+        exchange = part.exchange
+        x0 = x0_host[part.row0:part.row1].to(dev)
+
+    K, Wm = args.steps, args.warmup
+    method = args.method
+    per_step = RHS_PER_STEP[method]
+
+    def solve(k, y0, time_kernels=False, out=None):
+        if method == "dopri5":
+            t = torch.tensor([0.0, DT * (k - 0.5)], dtype=torch.float64)  # inside the k-th step: exactly k steps
+            return nb.odeint_fused(graph, spec, y0, t, method="dopri5", forced_dt=DT, terminal_only=True,
+                                   exchange=exchange, time_kernels=time_kernels, out=out)
+        t = torch.linspace(0, DT * k, k + 1, dtype=torch.float64)
+        return nb.odeint_fused(graph, spec, y0, t, method=method, terminal_only=True, exchange=exchange,
+                               time_kernels=time_kernels, out=out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    out_buf = torch.empty((graph.n_rows, H), dtype=torch.float32, device=dev)
+    # ---- warm-up (>= 3 steps, untimed) ----
+    solve(max(Wm, 1), x0, out=out_buf)
+    barrier()
+
+    # ---- timed region: exactly K steps, state resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    ev0.record()
+    yT = solve(K, x0, time_kernels=True, out=out_buf)
+    ev1.record()
+    barrier()
+    wall1 = time.time()
+    info = solver.last_solve_info
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(wall0, wall1)
+    if dist is not None:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    assert info.n_accepted == K and info.nfe == per_step * K + (1 if method == "dopri5" else 0), info
+    finite = bool(torch.isfinite(yT).all())
+    value = n * H * K / (ms * 1e-3)
+    launches = int(info.n_launches)
+
+    stage_ms = info.class_ms[_ffi.K_STAGE]
+    stage_n = info.class_launches[_ffi.K_STAGE]
+    stage_avg_ms = stage_ms / max(stage_n, 1)
+    n_rows_local = graph.n_rows
+    nnz_local = graph.nnz
+    algo_bytes = bytes_rhs(n_rows_local, nnz_local, H)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (stage_avg_ms * 1e-3) / 1e9 if stage_avg_ms > 0 else 0.0
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")))
+        if prof.get("nodes") == n and prof.get("hidden") == H and world == 1:
+            traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "kernel": "fused RHS stage kernel (CSR gather + W GEMM + bias/ReLU + RK stage epilogue)",
+        "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": stage_avg_ms, "launches_timed": int(stage_n),
+        "share_of_step": stage_ms / ms if ms > 0 else None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+        "class_ms": {"stage": info.class_ms[_ffi.K_STAGE], "algebra": info.class_ms[_ffi.K_ALGEBRA],
+                     "control": info.class_ms[_ffi.K_CONTROL], "emit": info.class_ms[_ffi.K_EMIT]},
+    }
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            from ndcn_b200 import workloads as wl
+            # the reference's own operator format at scale: uncoalesced fp32 sparse COO (utils.py:12-23);
+            # ODEFunc converts it to CSR on the GPU at its first use (the warm-up call below)
+            func = nb.ODEFunc(H, wl.to_reference_coo(phi))
+            func.wt.weight.data.copy_(W)
+            func.wt.bias.data.copy_(b)
+            func = func.to(dev).eval()
+            t_host = torch.tensor([0.0, DT * (K - 0.5)], dtype=torch.float64)
+            opts = {"forced_dt": DT} if method == "dopri5" else None
+            t_arg = t_host if method == "dopri5" else torch.linspace(0, DT * K, K + 1, dtype=torch.float64)
+
+            def e2e_call():
+                with torch.no_grad():
+                    return nb.odeint(func, x0_host, t_arg, method=method, options=opts, terminal_only=True)
+
+            e2e_call()  # warm-up of the host path (pageable result buffer, allocator)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            res = e2e_call()
+            torch.cuda.synchronize(dev)
+            e_s = time.perf_counter() - t0
+            assert res.device.type == "cpu" and res.shape == (n, H)
+            e2e = {"value": n * H * K / e_s, "unit": UNIT, "h2d_bytes_per_step": n * H * 4 / K,
+                   "d2h_bytes_per_step": n * H * 4 / K, "seconds": e_s,
+                   "note": "one ndcn_b200.odeint(ODEFunc, y0_pinned_host, t) call covering K steps; y0 H2D (%d B) and "
+                           "y(T) D2H (%d B) inside the timed region, bytes amortised over K steps" % (n * H * 4, n * H * 4)}
+        else:
+            # multi-GPU e2e: every rank stages its row block from pinned host memory and returns it
+            y_host = x0_host[part.row0:part.row1].contiguous().pin_memory()
+            r_host = torch.empty_like(y_host).pin_memory()
+            barrier()
+            t0 = time.perf_counter()
+            yd = y_host.to(dev, non_blocking=True)
+            r = solve(K, yd, out=out_buf)
+            r_host.copy_(r, non_blocking=True)
+            barrier()
+            e_s = time.perf_counter() - t0
+            tt = torch.tensor([e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_s = float(tt.item())
+            e2e = {"value": n * H * K / e_s, "unit": UNIT, "h2d_bytes_per_step": n * H * 4 / K,
+                   "d2h_bytes_per_step": n * H * 4 / K, "seconds": e_s,
+                   "note": "per-rank row blocks staged from pinned host memory and returned to it, whole job bytes"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 1),
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, n, nnz),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "solver": {"nfe": info.nfe, "accepted": info.n_accepted, "rejected": info.n_rejected, "finite": finite},
+    }
+    if world > 1:
+        line["config"]["parallelism"] = "1-D node-row partition x%d, NCCL halo exchange before every RHS eval" % world
+        line["partition"] = part.describe()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del x0, out_buf
+        torch.cuda.empty_cache()
+        res = cpu_reference_run(args, 2, 1, args.cpu_budget_s)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

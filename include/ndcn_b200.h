@@ -100,6 +100,18 @@ enum ndcn_method { NDCN_EULER = 0, NDCN_MIDPOINT = 1, NDCN_RK4 = 2, NDCN_DOPRI5 
 
 #define NDCN_O_TERMINAL_ONLY 1u /* out holds only y(t[-1])  (ODEBlock terminal=True)      */
 #define NDCN_O_FORCED_DT 2u     /* dopri5: every step accepted, dt = forced_dt            */
+#define NDCN_O_TIME_KERNELS 4u  /* bracket every launch with CUDA events on `s`; per-class sums
+                                   come back in ndcn_solve_stats_t (profiling aid for bench.py)   */
+
+/* kernel classes for ndcn_solve_stats_t::class_ms / class_launches */
+enum ndcn_kernel_class {
+  NDCN_K_STAGE = 0,   /* fused RHS + stage-algebra kernels (the dominant kernel) */
+  NDCN_K_ALGEBRA = 1, /* stage algebra on a k already in HBM (dopri5 pre-stage, callback RHS) */
+  NDCN_K_CONTROL = 2, /* step-size controller / scalar reductions */
+  NDCN_K_EMIT = 3,    /* dense output */
+  NDCN_K_INIT = 4,    /* initial-step norms */
+  NDCN_K_CLASSES = 8
+};
 
 typedef struct ndcn_solve_opts {
   int32_t method;   /* enum ndcn_method */
@@ -110,6 +122,9 @@ typedef struct ndcn_solve_opts {
   ndcn_exchange_callback_t exchange; /* NULL on one GPU */
   void* exchange_user;
   double safety, ifactor, dfactor; /* 0 => dopri5.py:60 defaults .9 / 10 / .2 */
+  double first_step;           /* > 0: initial dt given, _select_initial_step skipped (dopri5.py:79-82;
+                                  the reference replaces ANY user first_step by 0.01 -- the host layer
+                                  reproduces that quirk, the library takes the value as given)        */
 } ndcn_solve_opts_t;
 
 typedef struct ndcn_solve_stats {
@@ -122,6 +137,9 @@ typedef struct ndcn_solve_stats {
   double t_final;     /* end of last accepted step         */
   int32_t status;     /* NDCN_OK or an NDCN_E_* solver error */
   int32_t reserved;
+  double class_ms[8];        /* with NDCN_O_TIME_KERNELS: device time per kernel class, ms  */
+  int64_t class_launches[8]; /* ... and the launches that time covers (no-op launches of
+                                speculative attempts past the end are excluded)            */
 } ndcn_solve_stats_t;
 
 /* bytes of device workspace ndcn_solver_create needs for this problem */
@@ -151,6 +169,12 @@ int ndcn_rk_combine_f32(float* out, const float* y0, const float* const* k_host_
  * misc.py:146-157                                                                       */
 int ndcn_error_ratio_f32(const float* err, const float* y0, const float* y1, double rtol,
                          double atol, int64_t numel, double* sum_out_dev, ndcn_stream_t s);
+
+/* ---- multi-GPU plumbing ------------------------------------------------------------------
+ * out[i, :] = x[idx[i], :], i < n_idx: packs the boundary rows another rank needs into a
+ * contiguous send buffer (the reference is single-device; new with the 1-D row partition). */
+int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_idx, int32_t H, float* out,
+                       ndcn_stream_t s);
 
 /* library / build information */
 const char* ndcn_version(void);

@@ -27,7 +27,8 @@ RHS_NDCN, RHS_HEAT, RHS_GENE, RHS_MUTUAL, RHS_CALLBACK_KIND = 0, 1, 2, 3, 4
 F_NO_GRAPH, F_NO_CONTROL, F_NO_RELU = 1, 2, 4
 EULER, MIDPOINT, RK4, DOPRI5 = 0, 1, 2, 3
 METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4, "dopri5": DOPRI5}
-O_TERMINAL_ONLY, O_FORCED_DT = 1, 2
+O_TERMINAL_ONLY, O_FORCED_DT, O_TIME_KERNELS = 1, 2, 4
+K_STAGE, K_ALGEBRA, K_CONTROL, K_EMIT, K_INIT = 0, 1, 2, 3, 4
 
 
 class RhsDesc(C.Structure):
@@ -44,6 +45,7 @@ class SolveOpts(C.Structure):
         ("forced_dt", C.c_double), ("max_num_steps", C.c_int64),
         ("exchange", EXCHANGE_CALLBACK), ("exchange_user", C.c_void_p),
         ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double),
+        ("first_step", C.c_double),
     ]
 
 
@@ -52,6 +54,7 @@ class SolveStats(C.Structure):
         ("nfe", C.c_int64), ("n_accepted", C.c_int64), ("n_rejected", C.c_int64), ("n_launches", C.c_int64),
         ("first_step", C.c_double), ("last_dt", C.c_double), ("t_final", C.c_double),
         ("status", C.c_int32), ("reserved", C.c_int32),
+        ("class_ms", C.c_double * 8), ("class_launches", C.c_int64 * 8),
     ]
 
 
@@ -72,6 +75,7 @@ PROTOTYPES = {
                                       C.c_float, C.c_int64, C.c_void_p]),
     "ndcn_error_ratio_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int64,
                                        C.c_void_p, C.c_void_p]),
+    "ndcn_pack_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_version": (C.c_char_p, []),
     "ndcn_sm_arch": (C.c_int, []),
 }

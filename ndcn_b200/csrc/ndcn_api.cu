@@ -355,6 +355,36 @@ struct Driver {
   bool vec_ok;       // all elementwise buffers are 16-byte aligned and numel % 4 == 0 handled
   int64_t nfe = 0;
 
+  // ---- optional per-class kernel timing (NDCN_O_TIME_KERNELS): CUDA events on the launch stream
+  struct Ev { cudaEvent_t a, b; int cls; int64_t attempt; };
+  bool timing = false;
+  int64_t cur_attempt = -1;  // dopri5 attempt index the next launches belong to (-1: prologue)
+  std::vector<Ev> evs;
+  void t_begin(int cls) {
+    if (!timing) return;
+    Ev e{nullptr, nullptr, cls, cur_attempt};
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, st);
+    evs.push_back(e);
+  }
+  void t_end() {
+    if (timing) cudaEventRecord(evs.back().b, st);
+  }
+  // call after the stream is synchronised; launches of attempts >= n_real were device-side no-ops
+  void t_collect(int64_t n_real, ndcn_solve_stats_t* stats) {
+    for (Ev& e : evs) {
+      float ms = 0.f;
+      if (stats && (e.attempt < 0 || e.attempt < n_real) && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+        stats->class_ms[e.cls] += (double)ms;
+        stats->class_launches[e.cls] += 1;
+      }
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    evs.clear();
+  }
+
   EpiArgs blank() const {
     EpiArgs e;
     std::memset(&e, 0, sizeof(e));
@@ -380,7 +410,10 @@ struct Driver {
       return epi_only(pp(k_host), e2, n_partials);
     }
     sv->launches += 1;
-    return launch_stage(bind, src, e, n_partials, st);
+    t_begin(NDCN_K_STAGE);
+    const int rc = launch_stage(bind, src, e, n_partials, st);
+    t_end();
+    return rc;
   }
 
   int epi_only(PtrPair k_in, EpiArgs e, int* n_partials = nullptr) {
@@ -388,7 +421,9 @@ struct Driver {
     const int grid = grid_for_elems(sv->numel, sv->sm_count);
     if (n_partials) *n_partials = grid;
     sv->launches += 1;
+    t_begin(NDCN_K_ALGEBRA);
     k_epi_only<<<grid, kStageThreads, 0, st>>>(k_in, sv->numel, e, vec_ok ? 1 : 0);
+    t_end();
     return (int)cudaGetLastError();
   }
 
@@ -494,7 +529,9 @@ struct Dopri {
     const bool multi = d.o->exchange != nullptr;
     if (!multi) {
       sv->launches += 1;
+      d.t_begin(NDCN_K_CONTROL);
       k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 0);
+      d.t_end();
     } else {
       sv->launches += 2;
       k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 1);
@@ -547,7 +584,9 @@ struct Dopri {
     RC_TRY(d.stage(Yoth, Yq, e, KFq, &n_partials));
     RC_TRY(reduce_and_control(n_partials));
     sv->launches += 1;
+    d.t_begin(NDCN_K_EMIT);
     k_emit<<<grid_for_elems(sv->numel, sv->sm_count), kStageThreads, 0, d.st>>>(emit, d.vec_ok ? 1 : 0);
+    d.t_end();
     return (int)cudaGetLastError();
   }
 
@@ -591,7 +630,8 @@ struct Dopri {
     h.dfactor = (double)(float)(d.o->dfactor > 0 ? d.o->dfactor : 0.2);
     h.forced = forced ? 1 : 0;
     h.forced_dt = d.o->forced_dt;
-    h.dt = forced ? d.o->forced_dt : 0.0;
+    const bool given_first = !forced && d.o->first_step > 0.0;
+    h.dt = forced ? d.o->forced_dt : (given_first ? d.o->first_step : 0.0);
     h.first_step = h.dt;
     h.numel_global = (double)sv->numel;  // multi-GPU: overwritten below through the hook
     h.max_num_steps = d.o->max_num_steps > 0 ? d.o->max_num_steps : 2147483647LL;
@@ -627,7 +667,7 @@ struct Dopri {
 
     // f0 = func(t0, y0)     dopri5.py:78
     RC_TRY(d.stage(pp(sv->Y[0]), sv->Y[0], store_only(sv->KF[0]), sv->KF[0]));
-    if (!forced) {
+    if (!forced && !given_first) {
       // _select_initial_step(order=4)     dopri5.py:80, misc.py:84-143
       const int grid = grid_for_elems(sv->numel, sv->sm_count);
       sv->launches += 1;
@@ -650,10 +690,29 @@ struct Dopri {
     }
     CU_TRY(cudaGetLastError());
 
-    // attempts are enqueued in growing batches; kernels of attempts past the end are no-ops
+    // attempts are enqueued in growing batches; kernels of attempts past the end are no-ops.
+    // With a forced dt the host can replay the controller's float64 time accumulation, so
+    // exactly the needed attempts are enqueued and the controller is polled once at the end.
+    int64_t forced_left = -1;
+    if (forced) {
+      forced_left = 0;
+      double t1 = t[0];
+      while (t[n_t - 1] > t1 && forced_left < (int64_t)1 << 40) {
+        t1 += d.o->forced_dt;
+        ++forced_left;
+      }
+    }
     int batch = host_parity ? 1 : 2;
+    int64_t issued = 0;
     for (;;) {
-      for (int i = 0; i < batch; ++i) RC_TRY(attempt());
+      int n_now = batch;
+      if (forced_left >= 0 && !host_parity) n_now = (int)std::min<int64_t>(forced_left - issued, 64);
+      if (n_now < 1) n_now = 1;
+      for (int i = 0; i < n_now; ++i) {
+        d.cur_attempt = issued++;
+        RC_TRY(attempt());
+      }
+      if (forced_left >= 0 && !host_parity && issued < forced_left) continue;  // no poll needed yet
       RC_TRY(d.poll());
       const Ctrl& c = *sv->ctrl_host;
       par = c.parity;
@@ -676,6 +735,8 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   sv->launches = 0;
   Driver d{sv, opts, st, RhsBinding{sv->g, &sv->rhs, sv->Wt, sv->partials, sv->max_partials, sv->sm_count}, false, 0};
   d.vec_ok = aligned16(out) && aligned16(y0) && (sv->numel % 4 == 0);
+  d.timing = (opts->flags & NDCN_O_TIME_KERNELS) != 0;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
   std::memset(sv->ctrl_host, 0, sizeof(Ctrl));
 
   const bool fast_h = sv->H == 256 || sv->H == 128 || sv->H == 64 || sv->H == 32;
@@ -696,9 +757,18 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   } else {
     rc = run_fixed_grid(d, y0, t_host, n_t, out);
   }
+  if (d.timing) {
+    cudaStreamSynchronize(st);
+    d.t_collect(sv->method == NDCN_DOPRI5 ? (int64_t)sv->ctrl_host->n_attempt : (int64_t)1 << 60, stats);
+  }
   if (stats) {
     const Ctrl& c = *sv->ctrl_host;
-    stats->nfe = d.nfe;
+    // speculative attempts enqueued past the end are device-side no-ops: count the evaluations
+    // that really ran (f0 [+ the initial-step probe] + 6 per attempt the controller saw)
+    if (sv->method == NDCN_DOPRI5 && n_t > 1)
+      stats->nfe = (((opts->flags & NDCN_O_FORCED_DT) || opts->first_step > 0.0) ? 1 : 2) + 6 * (int64_t)c.n_attempt;
+    else
+      stats->nfe = d.nfe;
     stats->n_accepted = c.n_accept;
     stats->n_rejected = c.n_reject;
     stats->n_launches = sv->launches;
@@ -746,6 +816,17 @@ extern "C" int ndcn_error_ratio_f32(const float* err, const float* y0, const flo
   k_error_ratio<<<grid, kStageThreads, 0, st>>>(err, y0, y1, numel, (float)rtol, (float)atol, partials);
   k_sum_partials<<<1, kStageThreadsCtl, 0, st>>>(partials, grid, sum_out_dev);
   cudaFreeAsync(partials, st);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_idx, int32_t H, float* out,
+                                  ndcn_stream_t s) {
+  if (n_idx < 0 || H < 1 || (n_idx > 0 && (!x || !idx || !out))) return NDCN_E_ARG;
+  if (n_idx == 0) return NDCN_OK;
+  const int vec = (H % 4 == 0) && aligned16(x) && aligned16(out);
+  const int64_t blocks = (n_idx + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int grid = (int)std::min<int64_t>(blocks, 148 * 16);
+  k_pack_rows<<<grid, kStageThreads, 0, (cudaStream_t)s>>>(x, idx, n_idx, H, out, vec);
   return (int)cudaGetLastError();
 }
 

@@ -331,6 +331,28 @@ __global__ void __launch_bounds__(kStageThreadsCtl) k_sum_partials(const double*
   if (threadIdx.x == 0) *out = s;
 }
 
+// Halo pack for the multi-GPU exchange: out[i, :] = x[idx[i], :].  One warp per row, 16-byte
+// accesses when H % 4 == 0 (vec), so every warp moves one contiguous row segment per iteration.
+__global__ void __launch_bounds__(kStageThreads) k_pack_rows(const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                                             int64_t n_idx, int H, float* __restrict__ out, int vec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n_idx; i += nwarps) {
+    const float* src = x + (int64_t)__ldg(idx + i) * H;
+    float* dst = out + i * H;
+    if (vec) {
+      for (int c = lane * 4; c < H; c += 128) {
+        float v[4];
+        ldv<4>(src + c, v);
+        stv<4>(dst + c, v);
+      }
+    } else {
+      for (int c = lane; c < H; c += 32) dst[c] = src[c];
+    }
+  }
+}
+
 // W [n][k] -> Wt [k][n]   (once per solve; H*H elements)
 __global__ void k_transpose(const float* __restrict__ W, float* __restrict__ Wt, int H) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

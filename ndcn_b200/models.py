@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import odeint as _ode
+from .odeint import odeint as _odeint
 from . import solver as _solver
 from .autograd_solver import SpmmFn
 from .graph import cached_graph, require_cuda
@@ -92,7 +92,7 @@ class ODEBlock(nn.Module):
 
     def forward(self, vt, x):
         integration_time_vector = vt.type_as(x)  # rounds the grid to the state's dtype FIRST (:71)
-        return _ode.odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
+        return _odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
                            method=self.method, terminal_only=bool(self.terminal))
 
 
@@ -111,7 +111,7 @@ class ODEBlock2(nn.Module):
 
     def forward(self, x):
         integration_time_vector = self.integration_time_vector.type_as(x)
-        return _ode.odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
+        return _odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
                            method=self.method, terminal_only=bool(self.terminal))
 
 

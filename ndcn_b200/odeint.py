@@ -112,11 +112,27 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
         base = func
         t = -t
         func = lambda tt, yy: -base(-tt, yy)  # noqa: E731
-    unknown = {k: v for k, v in options.items() if k not in ("max_num_steps",)}
+    # solver options (dopri5.py:60-62): first_step, safety, ifactor, dfactor, max_num_steps; anything else
+    # is reported and ignored like the reference's _handle_unused_kwargs (misc.py:28-31).  `forced_dt`
+    # is an extension of this backend (fixed-size accepted dopri5 steps, error estimate still computed).
+    known = ("max_num_steps", "first_step", "safety", "ifactor", "dfactor", "forced_dt")
+    unknown = {k: v for k, v in options.items() if k not in known}
+    if unknown:
+        import warnings
+        warnings.warn("{}: Unexpected arguments {}".format(method, unknown))
     max_num_steps = int(options.get("max_num_steps", 0) or 0)
+    fused_kw = {}
+    if method == "dopri5":
+        if options.get("first_step") is not None:
+            fused_kw["first_step"] = 0.01  # dopri5.py:81-82: a user first_step is replaced by 0.01
+        for name in ("safety", "ifactor", "dfactor"):
+            if options.get(name) is not None:
+                fused_kw[name] = float(options[name])
+        if options.get("forced_dt") is not None:
+            fused_kw["forced_dt"] = float(options["forced_dt"])
 
     out = None
-    fusable = (y0.dim() == 2 and y0.dtype == torch.float32 and not unknown and not _needs_grad(func, y0))
+    fusable = (y0.dim() == 2 and y0.dtype == torch.float32 and not _needs_grad(func, y0))
     if fusable:
         dev = require_cuda(y0.device if y0.is_cuda else None)
         bound = recognise(func, int(y0.shape[1]), dev)
@@ -126,10 +142,14 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
                 raise RuntimeError("size mismatch: operator is %dx%d, state has %d rows" %
                                    (graph.n_rows, graph.n_cols, y0.shape[0]))
             res = solver.odeint_fused(graph, spec, y0.detach().to(dev), t, method=method, rtol=float(rtol),
-                                      atol=float(atol), terminal_only=terminal_only, max_num_steps=max_num_steps)
+                                      atol=float(atol), terminal_only=terminal_only, max_num_steps=max_num_steps,
+                                      **fused_kw)
             out = res if y0.is_cuda else res.to(y0.device)
     if out is None:
         require_cuda(y0.device if y0.is_cuda else None)
+        if fused_kw:
+            raise NotImplementedError("solver options %s are implemented on the fused path only (recognised RHS, "
+                                      "no gradients)" % sorted(fused_kw))
         kw = dict(max_num_steps=max_num_steps) if max_num_steps > 0 else {}
         out = autograd_solver.solve(func, y0, t, float(rtol), float(atol), method, **kw)
         if terminal_only:

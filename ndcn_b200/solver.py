@@ -78,6 +78,8 @@ class SolveInfo:
     last_dt: float = float("nan")
     t_final: float = float("nan")
     status: int = 0
+    class_ms: Tuple[float, ...] = ()       # with time_kernels=True: device ms per kernel class (_ffi.K_*)
+    class_launches: Tuple[int, ...] = ()
 
 
 last_solve_info: Optional[SolveInfo] = None
@@ -137,7 +139,9 @@ def spmm(graph: CsrGraph, x: torch.Tensor) -> torch.Tensor:
 def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tensor, *, method: str = "dopri5",
                  rtol: float = 1e-7, atol: float = 1e-9, terminal_only: bool = False,
                  forced_dt: Optional[float] = None, max_num_steps: int = 0,
-                 exchange: Optional[Callable] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 exchange: Optional[Callable] = None, out: Optional[torch.Tensor] = None,
+                 time_kernels: bool = False, first_step: Optional[float] = None, safety: float = 0.0,
+                 ifactor: float = 0.0, dfactor: float = 0.0) -> torch.Tensor:
     """``torchdiffeq.odeint`` for a recognised RHS, entirely inside the CUDA library.
 
     y0: [n_rows, H] fp32 CUDA.  t: 1-D float tensor (any device); the values are used as
@@ -174,10 +178,13 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
         assert out.shape == shape and out.is_cuda and out.is_contiguous() and out.dtype == torch.float32
     opts = _ffi.SolveOpts()
     opts.method = method_id
-    opts.flags = (_ffi.O_TERMINAL_ONLY if terminal_only else 0) | (_ffi.O_FORCED_DT if forced_dt is not None else 0)
+    opts.flags = (_ffi.O_TERMINAL_ONLY if terminal_only else 0) | (_ffi.O_FORCED_DT if forced_dt is not None else 0) \
+        | (_ffi.O_TIME_KERNELS if time_kernels else 0)
     opts.rtol, opts.atol = float(rtol), float(atol)
     opts.forced_dt = float(forced_dt) if forced_dt is not None else 0.0
     opts.max_num_steps = int(max_num_steps)
+    opts.first_step = float(first_step) if first_step is not None else 0.0
+    opts.safety, opts.ifactor, opts.dfactor = float(safety), float(ifactor), float(dfactor)
     if exchange is not None:
         cb = _ffi.EXCHANGE_CALLBACK(exchange)
         keep.append(cb)
@@ -210,6 +217,7 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
             if spec.callback is not None:
                 lib.ndcn_solver_destroy(handle)
     last_solve_info = SolveInfo(stats.nfe, stats.n_accepted, stats.n_rejected, stats.n_launches, stats.first_step,
-                                stats.last_dt, stats.t_final, stats.status)
+                                stats.last_dt, stats.t_final, stats.status, tuple(stats.class_ms),
+                                tuple(stats.class_launches))
     _ffi.check(rc, "ndcn_odeint_f32")
     return out

@@ -1,0 +1,90 @@
+"""CPU, world_size 2 (and 3) over gloo: the 1-D row partition's host logic and halo exchange.
+Each rank rebuilds Phi x for its row block from [local | halo] rows and the result must equal the
+global product; the error-norm all-reduce hook is exercised with CPU tensors."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ndcn_b200 import partition, workloads as wl
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, H, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        phi = wl.graph_operator(wl.power_law_adjacency(n, 3, seed=1), "norm_lap")
+        x = torch.from_numpy(np.random.RandomState(0).standard_normal((n, H)).astype(np.float32))
+        part = partition.RowPartition.build(phi, world, rank, torch.device("cpu"), H)
+        blk = part.block
+        buf = torch.zeros(part.n_local + part.n_halo, H)
+        buf[:part.n_local] = x[part.row0:part.row1]
+        part.fill_halo(buf)
+        # halo rows arrived in the order of halo_global
+        ok_halo = torch.equal(buf[part.n_local:], x[torch.from_numpy(blk.halo_global)])
+        local = sp.csr_matrix((blk.val, blk.col, blk.rowptr), shape=(part.n_local, part.n_local + part.n_halo))
+        mine = local @ buf.numpy()
+        ref = (phi @ x.numpy())[part.row0:part.row1]
+        ok_spmm = np.allclose(mine, ref, rtol=1e-5, atol=1e-6)
+        red = torch.tensor([float(rank + 1), float(part.n_local)], dtype=torch.float64)
+        dist.all_reduce(red)
+        ok_red = red.tolist() == [world * (world + 1) / 2, float(n)]
+        out_q.put((rank, ok_halo, ok_spmm, ok_red, part.n_halo, part.n_send, sum(part.send_counts)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(world):
+    n, H = 257, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, H, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_halo, ok_spmm, ok_red, n_halo, n_send, tot in res:
+        assert ok_halo and ok_spmm and ok_red, (rank, ok_halo, ok_spmm, ok_red)
+        assert n_halo > 0 and n_send == tot
+    # every halo row received somewhere was sent by someone
+    assert sum(r[4] for r in res) == sum(r[5] for r in res)
+
+
+def test_row_blocks_and_remap():
+    b = partition.row_blocks(10, 3)
+    assert b.tolist() == [0, 4, 7, 10]
+    phi = wl.graph_operator(wl.grid_adjacency(6), "norm_lap")
+    seen = 0
+    for r in range(3):
+        blk = partition.build_local_block(phi, 3, r)
+        assert blk.rowptr[-1] == len(blk.col) == len(blk.val)
+        assert blk.col.max() < blk.n_local + blk.n_halo
+        assert np.all(np.diff(blk.halo_global) > 0)
+        assert blk.recv_counts[r] == 0 and blk.recv_counts.sum() == blk.n_halo
+        seen += len(blk.val)
+    assert seen == phi.nnz
+
+
+def test_single_rank_partition_is_the_whole_graph():
+    phi = wl.graph_operator(wl.erdos_renyi_adjacency(100, 6, seed=2), "norm_lap")
+    blk = partition.build_local_block(phi, 1, 0)
+    assert blk.n_halo == 0 and blk.n_local == 100
+    assert np.array_equal(blk.col, phi.indices)
