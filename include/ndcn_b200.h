@@ -110,6 +110,7 @@ enum ndcn_kernel_class {
   NDCN_K_CONTROL = 2, /* step-size controller / scalar reductions */
   NDCN_K_EMIT = 3,    /* dense output */
   NDCN_K_INIT = 4,    /* initial-step norms */
+  NDCN_K_GATHER = 5,  /* chunk-major gather z = Phi x feeding the tcgen05 GEMM stage kernel */
   NDCN_K_CLASSES = 8
 };
 
@@ -175,6 +176,22 @@ int ndcn_error_ratio_f32(const float* err, const float* y0, const float* y1, dou
  * contiguous send buffer (the reference is single-device; new with the 1-D row partition). */
 int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_idx, int32_t H, float* out,
                        ndcn_stream_t s);
+
+/* ---- library configuration -------------------------------------------------------------
+ * Process-wide knobs (also read once from the environment: NDCN_STAGE_IMPL, NDCN_GATHER_CW,
+ * NDCN_UMMA_MIN_ROWS).  They select between kernel families that compute the same function;
+ * results agree within the fp32 parity tolerance (rtol 1e-4 / atol 1e-6).  New here: the
+ * reference has one code path (ATen).                                                      */
+#define NDCN_IMPL_AUTO 0 /* tcgen05 path for H in {128,256} from NDCN_CFG_UMMA_MIN_ROWS rows */
+#define NDCN_IMPL_SIMT 1 /* fused FP32-FMA stage kernel (gather + GEMM + epilogue in one launch) */
+#define NDCN_IMPL_UMMA 2 /* chunk-major gather + tcgen05 3xTF32 GEMM/epilogue kernel */
+enum ndcn_config_key {
+  NDCN_CFG_STAGE_IMPL = 0,   /* NDCN_IMPL_* */
+  NDCN_CFG_GATHER_CW = 1,    /* 0 auto, -1 one pass over full rows, 16/32/64 floats per chunk */
+  NDCN_CFG_UMMA_MIN_ROWS = 2
+};
+int ndcn_config_set(int32_t key, int64_t value);
+int64_t ndcn_config_get(int32_t key);
 
 /* library / build information */
 const char* ndcn_version(void);

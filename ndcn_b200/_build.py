@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libndcn_b200.so")
 SOURCES = ["ndcn_api.cu"]
-HEADERS = ["ndcn_common.cuh", "stage_kernels.cuh", "solver_kernels.cuh"]
+HEADERS = ["ndcn_common.cuh", "stage_kernels.cuh", "solver_kernels.cuh", "gather_kernels.cuh", "umma_kernels.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,9 +13,13 @@
 #include <new>
 #include <vector>
 
+#include <cstdlib>
+
 #include "ndcn_common.cuh"
 #include "solver_kernels.cuh"
 #include "stage_kernels.cuh"
+#include "gather_kernels.cuh"
+#include "umma_kernels.cuh"
 
 using namespace ndcn;
 
@@ -32,7 +36,57 @@ using namespace ndcn;
 
 struct ndcn_graph {
   GraphView v;
+  int32_t* long_rows = nullptr;  // rows with more than kLongRow entries (device)
+  int n_long = 0;
+  int max_deg = 0;
 };
+
+// ---------------------------------------------------------------------------------------
+// library configuration (ndcn_config_set / environment, read once)
+// ---------------------------------------------------------------------------------------
+struct Config {
+  int stage_impl = NDCN_IMPL_AUTO;  // which kernel family evaluates relu((Phi x) W^T + b)
+  int gather_cw = 0;                // 0 auto, -1 full-row gather, else chunk width in floats (16/32/64)
+  int64_t umma_min_rows = 8192;     // auto: tcgen05 path from this many rows
+};
+static Config& cfg() {
+  static Config c = [] {
+    Config k;
+    if (const char* v = std::getenv("NDCN_STAGE_IMPL")) k.stage_impl = std::atoi(v);
+    if (const char* v = std::getenv("NDCN_GATHER_CW")) k.gather_cw = std::atoi(v);
+    if (const char* v = std::getenv("NDCN_UMMA_MIN_ROWS")) k.umma_min_rows = std::atoll(v);
+    return k;
+  }();
+  return c;
+}
+
+extern "C" int ndcn_config_set(int32_t key, int64_t value) {
+  switch (key) {
+    case NDCN_CFG_STAGE_IMPL:
+      if (value < NDCN_IMPL_AUTO || value > NDCN_IMPL_UMMA) return NDCN_E_ARG;
+      cfg().stage_impl = (int)value;
+      return NDCN_OK;
+    case NDCN_CFG_GATHER_CW:
+      if (!(value == 0 || value == -1 || value == 16 || value == 32 || value == 64)) return NDCN_E_ARG;
+      cfg().gather_cw = (int)value;
+      return NDCN_OK;
+    case NDCN_CFG_UMMA_MIN_ROWS:
+      if (value < 0) return NDCN_E_ARG;
+      cfg().umma_min_rows = value;
+      return NDCN_OK;
+    default:
+      return NDCN_E_ARG;
+  }
+}
+
+extern "C" int64_t ndcn_config_get(int32_t key) {
+  switch (key) {
+    case NDCN_CFG_STAGE_IMPL: return cfg().stage_impl;
+    case NDCN_CFG_GATHER_CW: return cfg().gather_cw;
+    case NDCN_CFG_UMMA_MIN_ROWS: return cfg().umma_min_rows;
+    default: return NDCN_E_ARG;
+  }
+}
 
 // Dormand-Prince / Shampine tableau, torchdiffeq/_impl/dopri5.py:11-36 (doubles, cast to fp32
 // exactly where the reference's tensor*python-float multiplication does, misc.py:25)
@@ -54,6 +108,7 @@ static const double kDpMid[7] = {
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 static inline PtrPair pp(float* a) { return PtrPair{{a, a}}; }
 static inline PtrPair pp(float* a, float* b) { return PtrPair{{a, b}}; }
 
@@ -71,6 +126,8 @@ struct ndcn_solver {
   float* KF[2] = {nullptr, nullptr};  // f0 / k7 (FSAL pair)
   float* K[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* Wt = nullptr;
+  float* Z = nullptr;     // Phi x between the gather and the tcgen05 GEMM kernel
+  float* Wimg = nullptr;  // W split into tf32 hi/lo, swizzled K-atoms (k_prep_w_image)
   // library-owned control scratch
   double* partials = nullptr;
   int max_partials = 0;
@@ -140,6 +197,11 @@ static int launch_dyn(const DynArgs& a, EpiArgs& e, double avg_deg, int* grid_ou
   return (int)cudaGetLastError();
 }
 
+struct StageTimer {  // optional per-launch timing hook (Driver implements it)
+  virtual void begin(int cls) = 0;
+  virtual void end() = 0;
+};
+
 struct RhsBinding {  // everything needed to launch one RHS stage
   const ndcn_graph* g;
   const ndcn_rhs_desc_t* rhs;
@@ -147,7 +209,90 @@ struct RhsBinding {  // everything needed to launch one RHS stage
   double* partials;
   int max_partials;
   int sm_count;
+  float* Z = nullptr;           // [n_rows, H] scratch (tcgen05 path)
+  const float* Wimg = nullptr;  // tf32 hi/lo W image (tcgen05 path)
+  StageTimer* timer = nullptr;
+  int64_t* launches = nullptr;
 };
+
+// ---- chunk-major gather ------------------------------------------------------------------
+static bool fast_width(int H) { return H == 256 || H == 128 || H == 64 || H == 32; }
+
+// chunk width (floats) of the gather for this problem; 0 = one pass over full rows
+static int pick_gather_cw(int64_t n_cols, int H) {
+  if (H % 16 != 0) return 0;
+  const int want = cfg().gather_cw;
+  if (want < 0) return fast_width(H) ? 0 : 16;
+  if (want > 0) return (H % want == 0) ? want : 16;
+  const double state_mb = (double)n_cols * H * 4.0 / 1048576.0;
+  if (state_mb <= 96.0 && fast_width(H)) return 0;  // the whole state is (nearly) L2-resident
+  const int cands[3] = {64, 32, 16};
+  for (int cw : cands)
+    if (H % cw == 0 && (double)n_cols * cw * 4.0 / 1048576.0 <= 72.0) return cw;
+  return 16;
+}
+
+static int gather_grid(const ndcn_graph* g, int H, int cw) {
+  const int lpr = cw / 4;
+  const int rpc = (32 / lpr) * kWarpsPerCta;
+  const int64_t n_rb = (g->v.n_rows + rpc - 1) / rpc;
+  return (int)((H / cw) * (n_rb + g->n_long));
+}
+
+// z/k = [relu](Phi x) fused with epilogue e (NdcnArgs::flags: NO_RELU / NO_GRAPH honoured)
+static int launch_gather(const RhsBinding& b, const NdcnArgs& a, int H, EpiArgs& e, int* grid_out, cudaStream_t st) {
+  const int cw = pick_gather_cw(a.g.n_cols, H);
+  if (cw == 0) {
+    NdcnArgs a2 = a;
+    a2.flags |= NDCN_F_NO_CONTROL;
+    switch (H) {
+      case 256: return launch_ndcn_fast<4, 2>(a2, e, grid_out, st);
+      case 128: return launch_ndcn_fast<4, 1>(a2, e, grid_out, st);
+      case 64: return launch_ndcn_fast<2, 1>(a2, e, grid_out, st);
+      default: return launch_ndcn_fast<1, 1>(a2, e, grid_out, st);
+    }
+  }
+  const int lpr = cw / 4;
+  const int rpc = (32 / lpr) * kWarpsPerCta;
+  const int n_rb = (int)((a.g.n_rows + rpc - 1) / rpc);
+  const int grid = gather_grid(b.g, H, cw);
+  *grid_out = grid;
+  if (grid == 0) return 0;
+  switch (cw) {
+    case 64: k_stage_gather_chunk<64><<<grid, kStageThreads, 0, st>>>(a, H, n_rb, b.g->n_long, b.g->long_rows, e); break;
+    case 32: k_stage_gather_chunk<32><<<grid, kStageThreads, 0, st>>>(a, H, n_rb, b.g->n_long, b.g->long_rows, e); break;
+    default: k_stage_gather_chunk<16><<<grid, kStageThreads, 0, st>>>(a, H, n_rb, b.g->n_long, b.g->long_rows, e); break;
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- tcgen05 GEMM + epilogue ---------------------------------------------------------------
+template <int H>
+static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_out, cudaStream_t st) {
+  using Cf = UmmaCfg<H>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(k_stage_gemm_umma<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::kSmemBytes));
+    attr_set = true;
+  }
+  const int64_t n_tiles = (u.n_rows + kUmmaM - 1) / kUmmaM;
+  const int grid = (int)std::min<int64_t>(n_tiles, sm_count);
+  *grid_out = grid;
+  if (grid == 0) return 0;
+  k_stage_gemm_umma<H><<<grid, kUmmaThreads, Cf::kSmemBytes, st>>>(u, e);
+  return (int)cudaGetLastError();
+}
+
+static bool umma_eligible(const ndcn_rhs_desc_t& r, int64_t n_rows) {
+  if (r.kind != NDCN_RHS_NDCN || (r.flags & NDCN_F_NO_CONTROL)) return false;
+  if (r.H != 256 && r.H != 128) return false;
+  const int impl = cfg().stage_impl;
+  if (impl == NDCN_IMPL_SIMT) return false;
+  if (impl == NDCN_IMPL_UMMA) return true;
+  return n_rows >= cfg().umma_min_rows;
+}
+
+static EpiArgs store_only(float* out);
 
 // Launches f(src) fused with epilogue `e`; returns the number of per-CTA partial slots the
 // kernel writes in EPI_ERR mode through *n_partials.
@@ -156,6 +301,13 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
   e.partials = b.partials;
   int grid = 0;
   int rc = 0;
+  auto tick = [&](int cls) {
+    if (b.timer) b.timer->begin(cls);
+    if (b.launches) *b.launches += 1;
+  };
+  auto tock = [&]() {
+    if (b.timer) b.timer->end();
+  };
   if (r.kind == NDCN_RHS_NDCN) {
     NdcnArgs a;
     a.g = b.g->v;
@@ -165,18 +317,49 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
     a.flags = r.flags;
     const bool need_w = !(r.flags & NDCN_F_NO_CONTROL);
     if (need_w && (r.W == nullptr || r.b == nullptr)) return NDCN_E_ARG;
-    switch (r.H) {
-      case 256: rc = launch_ndcn_fast<4, 2>(a, e, &grid, st); break;
-      case 128: rc = launch_ndcn_fast<4, 1>(a, e, &grid, st); break;
-      case 64: rc = launch_ndcn_fast<2, 1>(a, e, &grid, st); break;
-      case 32: rc = launch_ndcn_fast<1, 1>(a, e, &grid, st); break;
-      default: {
-        if (r.H < 1 || r.H > 1024) return NDCN_E_ARG;
-        grid = (int)((a.g.n_rows + kWarpsPerCta - 1) / kWarpsPerCta);
-        const size_t smem = sizeof(float) * kWarpsPerCta * r.H;
-        k_stage_ndcn_any<<<grid, kStageThreads, smem, st>>>(a, r.H, r.W, e);
-        rc = (int)cudaGetLastError();
+    if (r.H < 1 || r.H > 1024) return NDCN_E_ARG;
+    const bool src_aligned = aligned16(src.p[0]) && aligned16(src.p[1]);
+    if (umma_eligible(r, a.g.n_rows) && b.Z != nullptr && b.Wimg != nullptr && src_aligned) {
+      // (1) z = Phi x  -> Z (skipped with no_graph)   (2) k = relu(z W^T + b) + stage epilogue
+      UmmaArgs u;
+      u.z = src;
+      if (!(r.flags & NDCN_F_NO_GRAPH)) {
+        NdcnArgs ga = a;
+        ga.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+        EpiArgs se = store_only(b.Z);
+        int g2 = 0;
+        tick(NDCN_K_GATHER);
+        rc = launch_gather(b, ga, r.H, se, &g2, st);
+        tock();
+        if (rc != 0) return rc;
+        u.z = pp(b.Z);
       }
+      u.wimg = b.Wimg;
+      u.bias = r.b;
+      u.n_rows = a.g.n_rows;
+      u.flags = r.flags;
+      tick(NDCN_K_STAGE);
+      rc = r.H == 256 ? launch_umma<256>(u, e, b.sm_count, &grid, st) : launch_umma<128>(u, e, b.sm_count, &grid, st);
+      tock();
+    } else if (!need_w && src_aligned && pick_gather_cw(a.g.n_cols, r.H) > 0) {
+      tick(NDCN_K_STAGE);
+      rc = launch_gather(b, a, r.H, e, &grid, st);
+      tock();
+    } else {
+      tick(NDCN_K_STAGE);
+      switch (r.H) {
+        case 256: rc = launch_ndcn_fast<4, 2>(a, e, &grid, st); break;
+        case 128: rc = launch_ndcn_fast<4, 1>(a, e, &grid, st); break;
+        case 64: rc = launch_ndcn_fast<2, 1>(a, e, &grid, st); break;
+        case 32: rc = launch_ndcn_fast<1, 1>(a, e, &grid, st); break;
+        default: {
+          grid = (int)((a.g.n_rows + kWarpsPerCta - 1) / kWarpsPerCta);
+          const size_t smem = sizeof(float) * kWarpsPerCta * r.H;
+          k_stage_ndcn_any<<<grid, kStageThreads, smem, st>>>(a, r.H, r.W, e);
+          rc = (int)cudaGetLastError();
+        }
+      }
+      tock();
     }
   } else if (r.kind == NDCN_RHS_HEAT || r.kind == NDCN_RHS_GENE || r.kind == NDCN_RHS_MUTUAL) {
     DynArgs a;
@@ -186,9 +369,11 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
     a.d = r.H;
     for (int i = 0; i < 8; ++i) a.p[i] = r.p[i];
     const double avg = a.g.n_rows > 0 ? (double)a.g.nnz / (double)a.g.n_rows : 0.0;
+    tick(NDCN_K_STAGE);
     if (r.kind == NDCN_RHS_HEAT) rc = launch_dyn<NDCN_RHS_HEAT>(a, e, avg, &grid, st);
     else if (r.kind == NDCN_RHS_GENE) rc = launch_dyn<NDCN_RHS_GENE>(a, e, avg, &grid, st);
     else rc = launch_dyn<NDCN_RHS_MUTUAL>(a, e, avg, &grid, st);
+    tock();
   } else {
     return NDCN_E_ARG;
   }
@@ -198,12 +383,19 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
   return 0;
 }
 
-static int max_partials_for(int64_t n_rows, int H) {
-  // upper bound over every stage kernel's grid: the [N,1] kernels with 4 lanes per row
-  int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32);  // warp per row / LPR=32
+static int max_partials_for(const ndcn_graph* g, int H) {
+  // upper bound over every stage kernel's grid: the [N,1] kernels with 4 lanes per row, the
+  // warp-per-row kernels, and the chunk-major gather (H/cw chunks x (row blocks + long rows))
+  const int64_t n_rows = g->v.n_rows;
+  int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32);
   int64_t by_lpr4 = (n_rows + 63) / 64;
-  (void)H;
-  return (int)std::max<int64_t>(std::max(by_rows, by_lpr4), 148 * 16) + 8;
+  int64_t best = std::max<int64_t>(std::max(by_rows, by_lpr4), 148 * 16);
+  if (H % 16 == 0) {
+    const int cws[3] = {16, 32, 64};
+    for (int cw : cws)
+      if (H % cw == 0) best = std::max<int64_t>(best, gather_grid(g, H, cw));
+  }
+  return (int)best + 8;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -222,11 +414,42 @@ extern "C" int ndcn_graph_create(int64_t n_rows, int64_t n_cols, int64_t nnz, co
   g->v.n_rows = n_rows;
   g->v.n_cols = n_cols;
   g->v.nnz = nnz;
+  // rows above kLongRow entries get their own CTAs in the chunk-major gather: list them once
+  if (n_rows > 0) {
+    std::vector<int32_t> rp((size_t)n_rows + 1);
+    cudaError_t ce = cudaMemcpy(rp.data(), rowptr, sizeof(int32_t) * (n_rows + 1), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) {
+      delete g;
+      return (int)ce;
+    }
+    std::vector<int32_t> longs;
+    for (int64_t r = 0; r < n_rows; ++r) {
+      const int deg = rp[r + 1] - rp[r];
+      if (deg < 0 || rp[r + 1] > nnz) {
+        delete g;
+        return NDCN_E_ARG;
+      }
+      g->max_deg = std::max(g->max_deg, deg);
+      if (deg > kLongRow) longs.push_back((int32_t)r);
+    }
+    g->n_long = (int)longs.size();
+    if (g->n_long > 0) {
+      ce = cudaMalloc((void**)&g->long_rows, sizeof(int32_t) * longs.size());
+      if (ce == cudaSuccess)
+        ce = cudaMemcpy(g->long_rows, longs.data(), sizeof(int32_t) * longs.size(), cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) {
+        if (g->long_rows) cudaFree(g->long_rows);
+        delete g;
+        return (int)ce;
+      }
+    }
+  }
   *out = g;
   return NDCN_OK;
 }
 
 extern "C" int ndcn_graph_destroy(ndcn_graph_t* g) {
+  if (g && g->long_rows) cudaFree(g->long_rows);
   delete g;
   return NDCN_OK;
 }
@@ -242,22 +465,48 @@ static EpiArgs store_only(float* out) {
   return e;
 }
 
+template <int H>
+static void prep_w_image(const float* W, float* img, cudaStream_t st) {
+  k_prep_w_image<H><<<(H * H + 255) / 256, 256, 0, st>>>(W, img);
+}
+
 extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x, float* out,
                                  ndcn_stream_t s) {
   if (!g || !rhs || !x || !out) return NDCN_E_ARG;
   cudaStream_t st = (cudaStream_t)s;
   float* Wt = nullptr;
-  const bool need_wt = rhs->kind == NDCN_RHS_NDCN && !(rhs->flags & NDCN_F_NO_CONTROL) &&
-                       (rhs->H == 256 || rhs->H == 128 || rhs->H == 64 || rhs->H == 32);
-  if (need_wt) {
+  float* Z = nullptr;
+  float* Wimg = nullptr;
+  const bool use_umma = umma_eligible(*rhs, g->v.n_rows) && aligned16(x) && aligned16(out);
+  const bool need_wt = rhs->kind == NDCN_RHS_NDCN && !(rhs->flags & NDCN_F_NO_CONTROL) && fast_width(rhs->H) && !use_umma;
+  if (need_wt || use_umma) {
     if (!rhs->W) return NDCN_E_ARG;
+  }
+  if (need_wt) {
     CU_TRY(cudaMallocAsync((void**)&Wt, sizeof(float) * rhs->H * rhs->H, st));
     const int n = rhs->H * rhs->H;
     k_transpose<<<(n + 255) / 256, 256, 0, st>>>(rhs->W, Wt, rhs->H);
   }
+  if (use_umma) {
+    CU_TRY(cudaMallocAsync((void**)&Wimg, sizeof(float) * 2 * rhs->H * rhs->H, st));
+    if (!(rhs->flags & NDCN_F_NO_GRAPH))
+      CU_TRY(cudaMallocAsync((void**)&Z, sizeof(float) * (size_t)g->v.n_rows * rhs->H, st));
+    if (rhs->H == 256) prep_w_image<256>(rhs->W, Wimg, st);
+    else prep_w_image<128>(rhs->W, Wimg, st);
+  }
   RhsBinding b{g, rhs, Wt, nullptr, 0, 148};
+  cudaDeviceGetAttribute(&b.sm_count, cudaDevAttrMultiProcessorCount, 0);
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&b.sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // without Z the dispatcher falls back to the SIMT kernels; no_graph needs no Z: give it a non-null tag
+  b.Z = use_umma ? (Z ? Z : out) : nullptr;
+  b.Wimg = Wimg;
   int rc = launch_stage(b, pp(const_cast<float*>(x)), store_only(out), nullptr, st);
   if (Wt) cudaFreeAsync(Wt, st);
+  if (Z) cudaFreeAsync(Z, st);
+  if (Wimg) cudaFreeAsync(Wimg, st);
   return rc;
 }
 
@@ -282,7 +531,11 @@ extern "C" size_t ndcn_solver_workspace_bytes(int64_t n_rows, int64_t n_cols, in
   b += 4 * state_bytes(n_cols, H);                      // Y[2], YS[2]
   b += 7 * state_bytes(n_rows, H);                      // KF[2], K[5]
   b += align_up(sizeof(float) * (size_t)H * H, 256);    // W^T
-  return b + 256;
+  if (H == 256 || H == 128) {                           // tcgen05 path: Z = Phi x, W image
+    b += state_bytes(n_rows, H);
+    b += align_up(sizeof(float) * 2 * (size_t)H * H, 1024);
+  }
+  return b + 1280;
 }
 
 extern "C" int ndcn_solver_create(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, int32_t method,
@@ -313,10 +566,15 @@ extern "C" int ndcn_solver_create(const ndcn_graph_t* g, const ndcn_rhs_desc_t* 
   for (int i = 0; i < 2; ++i) sv->KF[i] = take(state_bytes(n_rows, sv->H));
   for (int i = 0; i < 5; ++i) sv->K[i] = take(state_bytes(n_rows, sv->H));
   sv->Wt = take(align_up(sizeof(float) * (size_t)sv->H * sv->H, 256));
+  if (sv->H == 256 || sv->H == 128) {
+    sv->Z = take(state_bytes(n_rows, sv->H));
+    p = (unsigned char*)align_up((size_t)p, 1024);
+    sv->Wimg = take(align_up(sizeof(float) * 2 * (size_t)sv->H * sv->H, 1024));
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sv->sm_count, cudaDevAttrMultiProcessorCount, dev);
-  sv->max_partials = max_partials_for(n_rows, sv->H);
+  sv->max_partials = max_partials_for(g, sv->H);
   int rc = (int)cudaMalloc((void**)&sv->partials, sizeof(double) * 2 * sv->max_partials);
   if (!rc) rc = (int)cudaMalloc((void**)&sv->xchg, sizeof(double) * 4);
   if (!rc) rc = (int)cudaMalloc((void**)&sv->t_stage, sizeof(float) * 4);
@@ -347,19 +605,29 @@ extern "C" int ndcn_solver_destroy(ndcn_solver_t* sv) {
 // ---------------------------------------------------------------------------------------
 namespace {
 
-struct Driver {
+struct Driver : StageTimer {
   ndcn_solver* sv;
   const ndcn_solve_opts_t* o;
   cudaStream_t st;
   RhsBinding bind;
-  bool vec_ok;       // all elementwise buffers are 16-byte aligned and numel % 4 == 0 handled
+  bool vec_ok = false;  // all elementwise buffers are 16-byte aligned and numel % 4 == 0 handled
   int64_t nfe = 0;
+
+  Driver(ndcn_solver* sv_, const ndcn_solve_opts_t* o_, cudaStream_t st_) : sv(sv_), o(o_), st(st_) {
+    bind = RhsBinding{sv->g, &sv->rhs, sv->Wt, sv->partials, sv->max_partials, sv->sm_count};
+    bind.Z = sv->Z;
+    bind.Wimg = sv->Wimg;
+    bind.timer = this;
+    bind.launches = &sv->launches;
+  }
 
   // ---- optional per-class kernel timing (NDCN_O_TIME_KERNELS): CUDA events on the launch stream
   struct Ev { cudaEvent_t a, b; int cls; int64_t attempt; };
   bool timing = false;
   int64_t cur_attempt = -1;  // dopri5 attempt index the next launches belong to (-1: prologue)
   std::vector<Ev> evs;
+  void begin(int cls) override { t_begin(cls); }
+  void end() override { t_end(); }
   void t_begin(int cls) {
     if (!timing) return;
     Ev e{nullptr, nullptr, cls, cur_attempt};
@@ -409,11 +677,7 @@ struct Driver {
       e2.k_out = pp(nullptr);
       return epi_only(pp(k_host), e2, n_partials);
     }
-    sv->launches += 1;
-    t_begin(NDCN_K_STAGE);
-    const int rc = launch_stage(bind, src, e, n_partials, st);
-    t_end();
-    return rc;
+    return launch_stage(bind, src, e, n_partials, st);
   }
 
   int epi_only(PtrPair k_in, EpiArgs e, int* n_partials = nullptr) {
@@ -434,7 +698,6 @@ struct Driver {
   }
 };
 
-bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 // ---- fixed grid: euler / midpoint / rk4 (3/8) -------------------------------------------
 // solvers.py:79-99 with the default grid (= t cast to the state's dtype)
@@ -733,7 +996,7 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
     if (!(t_host[i + 1] > t_host[i])) return NDCN_E_ARG;  // misc.py:59-60
   cudaStream_t st = (cudaStream_t)s;
   sv->launches = 0;
-  Driver d{sv, opts, st, RhsBinding{sv->g, &sv->rhs, sv->Wt, sv->partials, sv->max_partials, sv->sm_count}, false, 0};
+  Driver d(sv, opts, st);
   d.vec_ok = aligned16(out) && aligned16(y0) && (sv->numel % 4 == 0);
   d.timing = (opts->flags & NDCN_O_TIME_KERNELS) != 0;
   if (stats) std::memset(stats, 0, sizeof(*stats));
@@ -746,6 +1009,11 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
     sv->launches += 1;
   }
   if (sv->rhs.kind == NDCN_RHS_NDCN && fast_h && !(aligned16(out) && aligned16(y0))) return NDCN_E_ARG;
+  if (umma_eligible(sv->rhs, sv->n_rows) && sv->Wimg) {
+    if (sv->H == 256) prep_w_image<256>(sv->rhs.W, sv->Wimg, st);
+    else prep_w_image<128>(sv->rhs.W, sv->Wimg, st);
+    sv->launches += 1;
+  }
 
   int rc = 0;
   if (n_t == 1) {

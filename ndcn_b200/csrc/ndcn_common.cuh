@@ -107,6 +107,11 @@ __device__ __forceinline__ bool epi_resolve(const EpiArgs& a, EpiCtx& c) {
   }
   c.mode = a.mode;
   c.n_prev = a.n_prev;
+  // the RK4 (3/8) epilogues read a fixed number of earlier stages (rk_common.py:75-78)
+  if (a.mode == EPI_RK4_1) c.n_prev = 0;
+  else if (a.mode == EPI_RK4_2) c.n_prev = 1;
+  else if (a.mode == EPI_RK4_3) c.n_prev = 2;
+  else if (a.mode == EPI_RK4_4) c.n_prev = 3;
   c.k_out = sel(a.k_out, par);
   c.y_out = sel(a.y_out, par);
   c.y0 = sel(a.y0, par);
@@ -160,32 +165,48 @@ __device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[VW])
 
 // ------------------------------------------------------------------------------------
 // The stage epilogue: consumes freshly computed k values (still in registers) for VW
-// consecutive elements starting at element offset `off`.
+// consecutive elements starting at element offset `off`.  Split in two phases so that a
+// caller can issue the loads of several element groups before doing any arithmetic
+// (memory-level parallelism); epi_apply() is load + math for one group.
 // ------------------------------------------------------------------------------------
 template <int VW>
-__device__ __forceinline__ void epi_apply(const EpiCtx& c, int64_t off, const float (&k)[VW],
-                                          double& err_acc) {
+struct EpiIn {
+  float y0[VW];
+  float y1[VW];
+  float kp[6][VW];
+};
+
+template <int VW>
+__device__ __forceinline__ void epi_load(const EpiCtx& c, int64_t off, EpiIn<VW>& in) {
+  if (c.mode == EPI_STORE) return;
+  ldv_stream<VW>(c.y0 + off, in.y0);
+  if (c.mode == EPI_ERR) ldv<VW>(c.y1 + off, in.y1);
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j < c.n_prev) ldv_stream<VW>(c.kprev[j] + off, in.kp[j]);
+}
+
+template <int VW>
+__device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const float (&k)[VW], const EpiIn<VW>& in,
+                                         double& err_acc) {
   if (c.k_out != nullptr) stv<VW>(c.k_out + off, k);
   if (c.mode == EPI_STORE) return;
 
   if (c.mode == EPI_LINCOMB) {
+    // y_out = y0 + sum_j (dt*beta_j) k_j, summed left to right from the first term
+    // (misc.py:22-25: sum() of the per-term products; rk_common.py:50)
     float acc[VW];
-    float y0v[VW];
-    ldv_stream<VW>(c.y0 + off, y0v);
     if (c.n_prev == 0) {
 #pragma unroll
       for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], k[i]);
     } else {
-      float kv[VW];
-      ldv_stream<VW>(c.kprev[0] + off, kv);
 #pragma unroll
-      for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], kv[i]);
+      for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], in.kp[0][i]);
 #pragma unroll
       for (int j = 1; j < 6; ++j) {
         if (j < c.n_prev) {
-          ldv_stream<VW>(c.kprev[j] + off, kv);
 #pragma unroll
-          for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], kv[i]));
+          for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], in.kp[j][i]));
         }
       }
       const float cf = c.coef_fresh;
@@ -194,7 +215,7 @@ __device__ __forceinline__ void epi_apply(const EpiCtx& c, int64_t off, const fl
     }
     float out[VW];
 #pragma unroll
-    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], acc[i]);
+    for (int i = 0; i < VW; ++i) out[i] = fadd(in.y0[i], acc[i]);
     stv<VW>(c.y_out + off, out);
     return;
   }
@@ -202,63 +223,56 @@ __device__ __forceinline__ void epi_apply(const EpiCtx& c, int64_t off, const fl
   if (c.mode == EPI_ERR) {
     // err = sum_j (dt*c_err_j) k_j (7 terms, k6 fresh)           rk_common.py:60
     // ratio = err / (atol + rtol*max(|y0|,|y1|)); sum ratio^2      misc.py:146-157
-    float acc[VW], kv[VW], y0v[VW], y1v[VW];
-    ldv_stream<VW>(c.kprev[0] + off, kv);
+    float acc[VW];
 #pragma unroll
-    for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], kv[i]);
+    for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], in.kp[0][i]);
 #pragma unroll
     for (int j = 1; j < 6; ++j) {
-      ldv_stream<VW>(c.kprev[j] + off, kv);
 #pragma unroll
-      for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], kv[i]));
+      for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], in.kp[j][i]));
     }
 #pragma unroll
     for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[6], k[i]));
-    ldv_stream<VW>(c.y0 + off, y0v);
-    ldv<VW>(c.y1 + off, y1v);
 #pragma unroll
     for (int i = 0; i < VW; ++i) {
-      float tol = fadd(c.atol, fmul(c.rtol, fmaxf(fabsf(y0v[i]), fabsf(y1v[i]))));
+      float tol = fadd(c.atol, fmul(c.rtol, fmaxf(fabsf(in.y0[i]), fabsf(in.y1[i]))));
       float r = fdiv(acc[i], tol);
       float r2 = fmul(r, r);
       // torch.max propagates NaN, fmaxf does not: keep the poison visible to the controller
-      if (!(r2 == r2) || y0v[i] != y0v[i] || y1v[i] != y1v[i]) r2 = __int_as_float(0x7fc00000);
+      if (!(r2 == r2) || in.y0[i] != in.y0[i] || in.y1[i] != in.y1[i]) r2 = __int_as_float(0x7fc00000);
       err_acc += (double)r2;
     }
     return;
   }
 
   // ---- RK4 (3/8 rule), literal operation order of rk_common.py:72-78 ----
-  float y0v[VW], out[VW];
-  ldv_stream<VW>(c.y0 + off, y0v);
+  float out[VW];
   const float dt = c.dt;
   if (c.mode == EPI_RK4_1) {
 #pragma unroll
-    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], fdiv(fmul(dt, k[i]), 3.0f));
+    for (int i = 0; i < VW; ++i) out[i] = fadd(in.y0[i], fdiv(fmul(dt, k[i]), 3.0f));
   } else if (c.mode == EPI_RK4_2) {
-    float k1[VW];
-    ldv_stream<VW>(c.kprev[0] + off, k1);
 #pragma unroll
-    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], fmul(dt, fadd(fdiv(k1[i], -3.0f), k[i])));
+    for (int i = 0; i < VW; ++i) out[i] = fadd(in.y0[i], fmul(dt, fadd(fdiv(in.kp[0][i], -3.0f), k[i])));
   } else if (c.mode == EPI_RK4_3) {
-    float k1[VW], k2[VW];
-    ldv_stream<VW>(c.kprev[0] + off, k1);
-    ldv_stream<VW>(c.kprev[1] + off, k2);
 #pragma unroll
-    for (int i = 0; i < VW; ++i) out[i] = fadd(y0v[i], fmul(dt, fadd(fsub(k1[i], k2[i]), k[i])));
+    for (int i = 0; i < VW; ++i) out[i] = fadd(in.y0[i], fmul(dt, fadd(fsub(in.kp[0][i], in.kp[1][i]), k[i])));
   } else {  // EPI_RK4_4
-    float k1[VW], k2[VW], k3[VW];
-    ldv_stream<VW>(c.kprev[0] + off, k1);
-    ldv_stream<VW>(c.kprev[1] + off, k2);
-    ldv_stream<VW>(c.kprev[2] + off, k3);
     const float dt8 = fdiv(dt, 8.0f);
 #pragma unroll
     for (int i = 0; i < VW; ++i) {
-      float s = fadd(fadd(fadd(k1[i], fmul(3.0f, k2[i])), fmul(3.0f, k3[i])), k[i]);
-      out[i] = fadd(y0v[i], fmul(s, dt8));
+      float s = fadd(fadd(fadd(in.kp[0][i], fmul(3.0f, in.kp[1][i])), fmul(3.0f, in.kp[2][i])), k[i]);
+      out[i] = fadd(in.y0[i], fmul(s, dt8));
     }
   }
   stv<VW>(c.y_out + off, out);
+}
+
+template <int VW>
+__device__ __forceinline__ void epi_apply(const EpiCtx& c, int64_t off, const float (&k)[VW], double& err_acc) {
+  EpiIn<VW> in;
+  epi_load<VW>(c, off, in);
+  epi_math<VW>(c, off, k, in, err_acc);
 }
 
 // per-CTA reduction of the error partials; every CTA writes its slot (zeros included)
