@@ -188,10 +188,16 @@ int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_idx, int32_
 enum ndcn_config_key {
   NDCN_CFG_STAGE_IMPL = 0,   /* NDCN_IMPL_* */
   NDCN_CFG_GATHER_CW = 1,    /* 0 auto, -1 one pass over full rows, 16/32/64 floats per chunk */
-  NDCN_CFG_UMMA_MIN_ROWS = 2
+  NDCN_CFG_UMMA_MIN_ROWS = 2,
+  NDCN_CFG_GATHER_VERSION = 3 /* chunk-major gather: 1 one row per lane group, 2 persistent CTAs + TMA-staged CSR */
 };
 int ndcn_config_set(int32_t key, int64_t value);
 int64_t ndcn_config_get(int32_t key);
+
+/* Profiling aid: when buf_dev is non-NULL, CTA 0 of every later tcgen05 stage-kernel launch
+ * writes a timeline into it: 4 roles (W loader, A producer, MMA issuer, epilogue) x 4096
+ * uint64 entries, entry 0 = count, then (event_code << 56 | SM clock).  NULL switches it off. */
+int ndcn_debug_umma_trace(void* buf_dev);
 
 /* library / build information */
 const char* ndcn_version(void);

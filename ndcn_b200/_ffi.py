@@ -30,7 +30,7 @@ METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4, "dopri5": DOPRI5}
 O_TERMINAL_ONLY, O_FORCED_DT, O_TIME_KERNELS = 1, 2, 4
 K_STAGE, K_ALGEBRA, K_CONTROL, K_EMIT, K_INIT, K_GATHER = 0, 1, 2, 3, 4, 5
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
-CFG_STAGE_IMPL, CFG_GATHER_CW, CFG_UMMA_MIN_ROWS = 0, 1, 2
+CFG_STAGE_IMPL, CFG_GATHER_CW, CFG_UMMA_MIN_ROWS, CFG_GATHER_VERSION = 0, 1, 2, 3
 
 
 class RhsDesc(C.Structure):
@@ -80,6 +80,7 @@ PROTOTYPES = {
     "ndcn_pack_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_config_set": (C.c_int, [C.c_int32, C.c_int64]),
     "ndcn_config_get": (C.c_int64, [C.c_int32]),
+    "ndcn_debug_umma_trace": (C.c_int, [C.c_void_p]),
     "ndcn_version": (C.c_char_p, []),
     "ndcn_sm_arch": (C.c_int, []),
 }
@@ -139,15 +140,18 @@ def check(rc: int, what: str = "ndcn call") -> None:
 
 
 def configure(stage_impl: Optional[int] = None, gather_cw: Optional[int] = None,
-              umma_min_rows: Optional[int] = None) -> dict:
+              umma_min_rows: Optional[int] = None, gather_version: Optional[int] = None) -> dict:
     """Process-wide kernel-family knobs (``ndcn_config_set``); returns the previous values."""
     h = lib()
     prev = {"stage_impl": int(h.ndcn_config_get(CFG_STAGE_IMPL)), "gather_cw": int(h.ndcn_config_get(CFG_GATHER_CW)),
-            "umma_min_rows": int(h.ndcn_config_get(CFG_UMMA_MIN_ROWS))}
+            "umma_min_rows": int(h.ndcn_config_get(CFG_UMMA_MIN_ROWS)),
+            "gather_version": int(h.ndcn_config_get(CFG_GATHER_VERSION))}
     if stage_impl is not None:
         check(h.ndcn_config_set(CFG_STAGE_IMPL, int(stage_impl)), "ndcn_config_set")
     if gather_cw is not None:
         check(h.ndcn_config_set(CFG_GATHER_CW, int(gather_cw)), "ndcn_config_set")
     if umma_min_rows is not None:
         check(h.ndcn_config_set(CFG_UMMA_MIN_ROWS, int(umma_min_rows)), "ndcn_config_set")
+    if gather_version is not None:
+        check(h.ndcn_config_set(CFG_GATHER_VERSION, int(gather_version)), "ndcn_config_set")
     return prev

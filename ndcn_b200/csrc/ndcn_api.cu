@@ -48,6 +48,7 @@ struct Config {
   int stage_impl = NDCN_IMPL_AUTO;  // which kernel family evaluates relu((Phi x) W^T + b)
   int gather_cw = 0;                // 0 auto, -1 full-row gather, else chunk width in floats (16/32/64)
   int64_t umma_min_rows = 8192;     // auto: tcgen05 path from this many rows
+  int gather_v = 2;                 // chunk-major gather flavour: 1 one row per lane group, 2 persistent + TMA-staged CSR
 };
 static Config& cfg() {
   static Config c = [] {
@@ -55,6 +56,7 @@ static Config& cfg() {
     if (const char* v = std::getenv("NDCN_STAGE_IMPL")) k.stage_impl = std::atoi(v);
     if (const char* v = std::getenv("NDCN_GATHER_CW")) k.gather_cw = std::atoi(v);
     if (const char* v = std::getenv("NDCN_UMMA_MIN_ROWS")) k.umma_min_rows = std::atoll(v);
+    if (const char* v = std::getenv("NDCN_GATHER_V")) k.gather_v = std::atoi(v);
     return k;
   }();
   return c;
@@ -74,6 +76,10 @@ extern "C" int ndcn_config_set(int32_t key, int64_t value) {
       if (value < 0) return NDCN_E_ARG;
       cfg().umma_min_rows = value;
       return NDCN_OK;
+    case NDCN_CFG_GATHER_VERSION:
+      if (value != 1 && value != 2) return NDCN_E_ARG;
+      cfg().gather_v = (int)value;
+      return NDCN_OK;
     default:
       return NDCN_E_ARG;
   }
@@ -84,6 +90,7 @@ extern "C" int64_t ndcn_config_get(int32_t key) {
     case NDCN_CFG_STAGE_IMPL: return cfg().stage_impl;
     case NDCN_CFG_GATHER_CW: return cfg().gather_cw;
     case NDCN_CFG_UMMA_MIN_ROWS: return cfg().umma_min_rows;
+    case NDCN_CFG_GATHER_VERSION: return cfg().gather_v;
     default: return NDCN_E_ARG;
   }
 }
@@ -154,9 +161,13 @@ template <int VW, int NCH>
 static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaStream_t st) {
   const int64_t n = a.g.n_rows;
   if (a.flags & NDCN_F_NO_CONTROL) {
-    const int grid = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta);
+    const int n_long = (a.flags & NDCN_F_NO_GRAPH) ? 0 : a.n_long;
+    const int grid = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta) + n_long;
     *grid_out = grid;
-    k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
+    // H=256: 4 CTAs/SM (64 registers) x 4 row loads in flight per lane measured best on B200
+    // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
+    if constexpr (VW == 4 && NCH == 2) k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
+    else k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
   } else {
     using S = GemmSmem<VW, NCH>;
     static bool attr_set = false;
@@ -224,12 +235,18 @@ static int pick_gather_cw(int64_t n_cols, int H) {
   const int want = cfg().gather_cw;
   if (want < 0) return fast_width(H) ? 0 : 16;
   if (want > 0) return (H % want == 0) ? want : 16;
-  const double state_mb = (double)n_cols * H * 4.0 / 1048576.0;
-  if (state_mb <= 96.0 && fast_width(H)) return 0;  // the whole state is (nearly) L2-resident
+  // measured on B200 (profiles/README.md, round 1): without a way to pin the [N, cw] slab in L2 the
+  // chunk-major order does not beat one pass over full rows, so auto = full rows whenever the width
+  // has a full-row kernel
+  if (fast_width(H)) return 0;
   const int cands[3] = {64, 32, 16};
   for (int cw : cands)
     if (H % cw == 0 && (double)n_cols * cw * 4.0 / 1048576.0 <= 72.0) return cw;
   return 16;
+}
+
+static bool gather_uses_v2(int cw, uint32_t flags) {
+  return cfg().gather_v == 2 && (cw == 32 || cw == 64) && !(flags & NDCN_F_NO_GRAPH);
 }
 
 static int gather_grid(const ndcn_graph* g, int H, int cw) {
@@ -251,6 +268,23 @@ static int launch_gather(const RhsBinding& b, const NdcnArgs& a, int H, EpiArgs&
       case 64: return launch_ndcn_fast<2, 1>(a2, e, grid_out, st);
       default: return launch_ndcn_fast<1, 1>(a2, e, grid_out, st);
     }
+  }
+  if (gather_uses_v2(cw, a.flags)) {
+    const int n_blocks = (int)((a.g.n_rows + kG2Rows - 1) / kG2Rows);
+    const int64_t total = (int64_t)(H / cw) * (n_blocks + b.g->n_long);
+    const bool store_only = e.mode == EPI_STORE;
+    const int grid = (int)std::min<int64_t>(total, (int64_t)b.sm_count * (store_only ? 3 : 2));
+    *grid_out = grid;
+    if (grid == 0) return 0;
+    if (cw == 64 && store_only)
+      k_stage_gather_v2<64, true><<<grid, kG2Threads, 0, st>>>(a, H, n_blocks, b.g->n_long, b.g->long_rows, e);
+    else if (cw == 64)
+      k_stage_gather_v2<64, false><<<grid, kG2Threads, 0, st>>>(a, H, n_blocks, b.g->n_long, b.g->long_rows, e);
+    else if (store_only)
+      k_stage_gather_v2<32, true><<<grid, kG2Threads, 0, st>>>(a, H, n_blocks, b.g->n_long, b.g->long_rows, e);
+    else
+      k_stage_gather_v2<32, false><<<grid, kG2Threads, 0, st>>>(a, H, n_blocks, b.g->n_long, b.g->long_rows, e);
+    return (int)cudaGetLastError();
   }
   const int lpr = cw / 4;
   const int rpc = (32 / lpr) * kWarpsPerCta;
@@ -315,6 +349,8 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
     a.Wt = b.Wt;
     a.bias = r.b;
     a.flags = r.flags;
+    a.long_rows = b.g->long_rows;
+    a.n_long = b.g->n_long;
     const bool need_w = !(r.flags & NDCN_F_NO_CONTROL);
     if (need_w && (r.W == nullptr || r.b == nullptr)) return NDCN_E_ARG;
     if (r.H < 1 || r.H > 1024) return NDCN_E_ARG;
@@ -327,6 +363,7 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
         NdcnArgs ga = a;
         ga.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
         EpiArgs se = store_only(b.Z);
+        se.ctrl = e.ctrl;  // same buffer parity / done flag as the stage that consumes Z
         int g2 = 0;
         tick(NDCN_K_GATHER);
         rc = launch_gather(b, ga, r.H, se, &g2, st);
@@ -338,6 +375,13 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
       u.bias = r.b;
       u.n_rows = a.g.n_rows;
       u.flags = r.flags;
+      {
+        static const uint32_t dbg = [] {
+          const char* v = std::getenv("NDCN_UMMA_DBG");
+          return v ? (uint32_t)std::atoi(v) : 0u;
+        }();
+        u.dbg = dbg;
+      }
       tick(NDCN_K_STAGE);
       rc = r.H == 256 ? launch_umma<256>(u, e, b.sm_count, &grid, st) : launch_umma<128>(u, e, b.sm_count, &grid, st);
       tock();
@@ -387,7 +431,7 @@ static int max_partials_for(const ndcn_graph* g, int H) {
   // upper bound over every stage kernel's grid: the [N,1] kernels with 4 lanes per row, the
   // warp-per-row kernels, and the chunk-major gather (H/cw chunks x (row blocks + long rows))
   const int64_t n_rows = g->v.n_rows;
-  int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32);
+  int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32) + g->n_long;
   int64_t by_lpr4 = (n_rows + 63) / 64;
   int64_t best = std::max<int64_t>(std::max(by_rows, by_lpr4), 148 * 16);
   if (H % 16 == 0) {
@@ -1096,6 +1140,11 @@ extern "C" int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_
   const int grid = (int)std::min<int64_t>(blocks, 148 * 16);
   k_pack_rows<<<grid, kStageThreads, 0, (cudaStream_t)s>>>(x, idx, n_idx, H, out, vec);
   return (int)cudaGetLastError();
+}
+
+extern "C" int ndcn_debug_umma_trace(void* buf_dev) {
+  unsigned long long* p = (unsigned long long*)buf_dev;
+  return (int)cudaMemcpyToSymbol(g_umma_trace, &p, sizeof(p));
 }
 
 extern "C" const char* ndcn_version(void) { return "ndcn_b200 0.1.0 (sm_100a)"; }

@@ -23,18 +23,18 @@ constexpr int kKChunk = 16;     // W^T rows per TMA bulk chunk
 // Accumulation order along the row is the CSR order, i.e. the order torch.sparse.mm's COO
 // worker visits a row's entries on the CPU.
 // ---------------------------------------------------------------------------------------
-template <int VW, int NCH>
-__device__ __forceinline__ void gather_row(const GraphView& g, int64_t row, const float* __restrict__ x,
-                                           int lane, float (&acc)[NCH][VW]) {
+// Entries [start, end) of one row, visited in batches of 32 starting at `start` with a stride of
+// `batch_stride` entries (32 for a whole row; 32 * n_warps when the warps of a CTA share a long row).
+template <int VW, int NCH, int U = 4>
+__device__ __forceinline__ void gather_range(const GraphView& g, int start, int end, int batch_stride,
+                                             const float* __restrict__ x, int lane, float (&acc)[NCH][VW]) {
   constexpr int H = 32 * VW * NCH;
-  constexpr int U = 4;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
     for (int i = 0; i < VW; ++i) acc[ch][i] = 0.f;
-  const int start = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
   const float* xl = x + lane * VW;
-  for (int base = start; base < end; base += 32) {
+  for (int base = start; base < end; base += batch_stride) {
     const int idx = base + lane;
     int my_c = 0;
     float my_v = 0.f;
@@ -78,44 +78,96 @@ __device__ __forceinline__ void gather_row(const GraphView& g, int64_t row, cons
   }
 }
 
+template <int VW, int NCH>
+__device__ __forceinline__ void gather_row(const GraphView& g, int64_t row, const float* __restrict__ x,
+                                           int lane, float (&acc)[NCH][VW]) {
+  const int start = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
+  gather_range<VW, NCH>(g, start, end, 32, x, lane, acc);
+}
+
+constexpr int kLongRow = 256;  // entries; rows above this are shared by all warps of a CTA
+
 struct NdcnArgs {
   GraphView g;
   PtrPair x;          // gather source [n_cols, H] (parity-selected)
   const float* Wt;    // [H(k), H(n)] = W^T, row-major (prepared once per solve)
   const float* bias;  // [H]
   uint32_t flags;     // NDCN_F_*
+  const int32_t* long_rows;  // rows with more than kLongRow entries (may be null)
+  int n_long;
 };
 
 // ---------------------------------------------------------------------------------------
 // no_control / plain SpMM: one warp per row, k = [relu](Phi x) (or relu(x) with no_graph),
 // epilogue straight from the gather registers.
 // ---------------------------------------------------------------------------------------
-template <int VW, int NCH>
-__global__ void __launch_bounds__(kStageThreads) k_stage_ndcn_row(NdcnArgs a, EpiArgs e) {
+// Power-law hubs (degree ~ m sqrt(N), thousands of entries) would keep a single warp busy long
+// after every other row is done: rows above kLongRow entries are skipped by the row-per-warp
+// CTAs and handled by the first n_long CTAs of the grid, whose 8 warps interleave 32-entry
+// batches of the row and add their partial sums in warp order (fixed, reproducible).
+template <int VW, int NCH, int U = 4, int MINB = 3>
+__global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs a, EpiArgs e) {
   constexpr int H = 32 * VW * NCH;
+  __shared__ float s_part[kWarpsPerCta][H];
   EpiCtx c;
   if (!epi_resolve(e, c)) return;
   const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
   const float* __restrict__ x = sel(a.x, par);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool relu = !(a.flags & NDCN_F_NO_RELU);
+  const bool graph = !(a.flags & NDCN_F_NO_GRAPH);
+  const int n_long = graph ? a.n_long : 0;
   double err_acc = 0.0;
-  const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-  if (row < a.g.n_rows) {
+  if ((int)blockIdx.x < n_long) {
+    const int64_t row = __ldg(a.long_rows + blockIdx.x);
+    const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
     float acc[NCH][VW];
-    if (a.flags & NDCN_F_NO_GRAPH) {
+    gather_range<VW, NCH, U>(a.g, start + warp * 32, end, 32 * kWarpsPerCta, x, lane, acc);
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) ldv<VW>(x + row * H + ch * 32 * VW + lane * VW, acc[ch]);
-    } else {
-      gather_row<VW, NCH>(a.g, row, x, lane, acc);
-    }
-    const bool relu = !(a.flags & NDCN_F_NO_RELU);
+    for (int ch = 0; ch < NCH; ++ch) stv<VW>(&s_part[warp][ch * 32 * VW + lane * VW], acc[ch]);
+    __syncthreads();
+    if (warp == 0) {
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (relu) {
+      for (int ch = 0; ch < NCH; ++ch) {
+        float tot[VW];
 #pragma unroll
-        for (int i = 0; i < VW; ++i) acc[ch][i] = fmaxf(acc[ch][i], 0.f);
+        for (int i = 0; i < VW; ++i) tot[i] = 0.f;
+        for (int w = 0; w < kWarpsPerCta; ++w) {
+          float p[VW];
+          ldv<VW>(&s_part[w][ch * 32 * VW + lane * VW], p);
+#pragma unroll
+          for (int i = 0; i < VW; ++i) tot[i] += p[i];
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < VW; ++i) tot[i] = fmaxf(tot[i], 0.f);
+        }
+        epi_apply<VW>(c, row * H + ch * 32 * VW + lane * VW, tot, err_acc);
       }
-      epi_apply<VW>(c, row * H + ch * 32 * VW + lane * VW, acc[ch], err_acc);
+    }
+  } else {
+    const int64_t row = (int64_t)(blockIdx.x - n_long) * kWarpsPerCta + warp;
+    if (row < a.g.n_rows) {
+      float acc[NCH][VW];
+      bool mine = true;
+      if (!graph) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) ldv<VW>(x + row * H + ch * 32 * VW + lane * VW, acc[ch]);
+      } else {
+        const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
+        if (n_long > 0 && end - start > kLongRow) mine = false;  // produced by a long-row CTA
+        else gather_range<VW, NCH, U>(a.g, start, end, 32, x, lane, acc);
+      }
+      if (mine) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < VW; ++i) acc[ch][i] = fmaxf(acc[ch][i], 0.f);
+          }
+          epi_apply<VW>(c, row * H + ch * 32 * VW + lane * VW, acc[ch], err_acc);
+        }
+      }
     }
   }
   epi_finish_block(e, err_acc);

@@ -33,8 +33,27 @@ constexpr int kUmmaProdWarp0 = 10;
 constexpr int kUmmaProdWarps = 4;
 constexpr int kUmmaThreads = 32 * (kUmmaProdWarp0 + kUmmaProdWarps);  // 448
 constexpr int kUmmaStages = 2;
-constexpr int kUmmaStagePitch = 33;  // floats; per-warp 32x32 transpose tile, conflict-free both ways
-constexpr int kUmmaEpiRows = 8;      // rows whose epilogue loads are in flight together
+constexpr int kUmmaStagePitch = 32;  // floats; per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
+constexpr int kUmmaEpiBatch = 2;     // groups of 4 rows whose epilogue loads are in flight together
+
+// Optional device-side timeline of CTA 0 (ndcn_debug_umma_trace): per role a list of
+// (event << 56 | clock64) entries; profiling aid, null in production.
+constexpr int kTraceRoleCap = 4096;
+__device__ unsigned long long* g_umma_trace = nullptr;
+struct Tracer {
+  unsigned long long* p;
+  int n;
+  __device__ __forceinline__ Tracer(int role) : p(nullptr), n(0) {
+    unsigned long long* t = g_umma_trace;
+    if (t != nullptr && role >= 0 && blockIdx.x == 0) p = t + (size_t)role * kTraceRoleCap;
+  }
+  __device__ __forceinline__ void ev(int code) {
+    if (p != nullptr && n < kTraceRoleCap - 1) {
+      p[1 + n++] = ((unsigned long long)code << 56) | ((unsigned long long)clock64() & 0x00ffffffffffffffull);
+      p[0] = (unsigned long long)n;
+    }
+  }
+};
 
 template <int H>
 struct UmmaCfg {
@@ -88,8 +107,33 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// TMA-engine flavour: 128 bytes starting at p (16-byte aligned) into L2, no LSU slot involved
+__device__ __forceinline__ void prefetch_l2_bulk128(const void* p) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(p) : "memory");
+}
+
+// L2 prefetch of the 128-byte line that holds elements [off, off + 32) of every stream the
+// epilogue will read (one line per lane and stream): the later loads then see L2 latency, not
+// HBM latency, so a handful of registers per lane is enough to keep the memory system busy.
+__device__ __forceinline__ void epi_prefetch_l2(const EpiCtx& c, int64_t off, bool bulk) {
+  if (c.mode == EPI_STORE) return;
+  if (bulk) {
+    prefetch_l2_bulk128(c.y0 + off);
+    if (c.mode == EPI_ERR) prefetch_l2_bulk128(c.y1 + off);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < c.n_prev) prefetch_l2_bulk128(c.kprev[j] + off);
+  } else {
+    prefetch_l2(c.y0 + off);
+    if (c.mode == EPI_ERR) prefetch_l2(c.y1 + off);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < c.n_prev) prefetch_l2(c.kprev[j] + off);
+  }
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -131,6 +175,8 @@ struct UmmaArgs {
   const float* bias;  // [H]
   int64_t n_rows;
   uint32_t flags;     // NDCN_F_NO_RELU
+  uint32_t dbg;       // experiment switches (NDCN_UMMA_DBG): 1 no epilogue prefetch, 2 bulk (TMA) prefetch,
+                      // 4 prefetch lead 1 chunk instead of 2, 8 no producer prefetch
 };
 
 template <int H>
@@ -185,18 +231,35 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     // =========================== epilogue ===========================
     const int q = warp & 3;        // TMEM lane quadrant this warp may read
     const int half = warp >> 2;    // which half of the H columns
-    float* st = staging + warp * 32 * kUmmaStagePitch;
+    float4* st4 = reinterpret_cast<float4*>(staging + warp * 32 * kUmmaStagePitch);
     const bool relu = !(a.flags & NDCN_F_NO_RELU);
+    const int rsub = lane >> 3;    // after the transpose: 8 lanes x 16 bytes per row, 4 rows per instruction
+    const int cg = lane & 7;
+    constexpr int kChunks = H / 2 / 32;
+    // L2 prefetch lead in chunks: 1 measured best (2 thrashes L2 at the wide stages: 8 streams x
+    // 2 chunks x 148 SMs ~ 78 MB in flight; dbg bit 4 selects 2 for experiments)
+    const int kAhead = (a.dbg & 4u) ? 2 : 1;
+    const bool pf_on = !(a.dbg & 1u), pf_bulk = (a.dbg & 2u) != 0;
+    Tracer tr(warp == 0 && lane == 0 ? 3 : -1000000);
+    // lane r prefetches row r of this warp's quadrant for chunk number g of the warp's own sequence
+    auto prefetch_chunk = [&](int64_t g) {
+      const int64_t ti = g / kChunks;
+      if (ti >= my_tiles || !pf_on) return;
+      const int64_t row = ((int64_t)blockIdx.x + ti * gridDim.x) * kUmmaM + q * 32 + lane;
+      if (row < a.n_rows) epi_prefetch_l2(c, row * H + half * (H / 2) + (int)(g % kChunks) * 32, pf_bulk);
+    };
+    for (int g = 0; g < kAhead; ++g) prefetch_chunk(g);
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
       const int acc = (int)(i & 1);
       const int64_t row_base = tile * kUmmaM + q * 32;
       mbar_wait(&tmem_full[acc], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      constexpr int kChunks = H / 2 / 32;
+      tr.ev(6);
 #pragma unroll 1
       for (int cc = 0; cc < kChunks; ++cc) {
         const int c0 = half * (H / 2) + cc * 32;
+        prefetch_chunk(i * kChunks + cc + kAhead);
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + c0), v);
         if (cc == kChunks - 1) {
@@ -205,32 +268,39 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        // thread = row: park the 32 accumulators of this row in the transpose tile
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float kv = __uint_as_float(v[j]) + bias_s[c0 + j];
-          if (relu) kv = fmaxf(kv, 0.f);
-          st[lane * kUmmaStagePitch + j] = kv;
-        }
+        for (int j = 0; j < 8; ++j)
+          st4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        // lane = column c0 + lane; rows in groups of kUmmaEpiRows with all loads issued first
+        // lane = (row rsub of a group of 4, columns c0 + 4 cg .. +3): 128-byte segments, 16 bytes per lane
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * cg);
 #pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += kUmmaEpiRows) {
-          EpiIn<1> in[kUmmaEpiRows];
+        for (int it0 = 0; it0 < 8; it0 += kUmmaEpiBatch) {
+          EpiIn<4> in[kUmmaEpiBatch];
 #pragma unroll
-          for (int r = 0; r < kUmmaEpiRows; ++r) {
-            const int64_t row = row_base + r0 + r;
-            if (row < a.n_rows) epi_load<1>(c, row * H + c0 + lane, in[r]);
+          for (int u = 0; u < kUmmaEpiBatch; ++u) {
+            const int64_t row = row_base + (it0 + u) * 4 + rsub;
+            if (row < a.n_rows) epi_load<4>(c, row * H + c0 + 4 * cg, in[u]);
           }
 #pragma unroll
-          for (int r = 0; r < kUmmaEpiRows; ++r) {
-            const int64_t row = row_base + r0 + r;
+          for (int u = 0; u < kUmmaEpiBatch; ++u) {
+            const int r = (it0 + u) * 4 + rsub;
+            const int64_t row = row_base + r;
             if (row < a.n_rows) {
-              float kv[1] = {st[(r0 + r) * kUmmaStagePitch + lane]};
-              epi_math<1>(c, row * H + c0 + lane, kv, in[r], err_acc);
+              const float4 kk = st4[r * 8 + (cg ^ (r & 7))];
+              float kv[4] = {kk.x + b4.x, kk.y + b4.y, kk.z + b4.z, kk.w + b4.w};
+              if (relu) {
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) kv[e4] = fmaxf(kv[e4], 0.f);
+              }
+              epi_math<4>(c, row * H + c0 + 4 * cg, kv, in[u], err_acc);
             }
           }
         }
         __syncwarp();  // the transpose tile is rewritten by the next chunk
+        tr.ev(7);
       }
     }
   } else if (warp == kUmmaMmaWarp) {
@@ -238,16 +308,19 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = tf32, both K-major, N = H, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((128u >> 4) << 24);
+      Tracer tr(2);
       uint32_t it = 0;
       for (int64_t i = 0; i < my_tiles; ++i) {
         const int acc = (int)(i & 1);
         mbar_wait(&tmem_empty[acc], (uint32_t)(((i >> 1) & 1) ^ 1));
         tc_fence_after();
+        tr.ev(5);
         const uint32_t d_tmem = tmem + (uint32_t)(acc * H);
         for (int atom = 0; atom < Cf::kAtoms; ++atom, ++it) {
           const int s = it % kUmmaStages;
           mbar_wait(&full[s], (it / kUmmaStages) & 1);
           tc_fence_after();
+          tr.ev(3);
           const uint32_t sa = smem_u32(smem + s * Cf::kStageBytes);
           const uint32_t a_hi = sa, a_lo = sa + Cf::kABytes;
           const uint32_t b_hi = sa + 2 * Cf::kABytes, b_lo = b_hi + Cf::kBBytes;
@@ -260,6 +333,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
             umma_tf32(d_tmem, dah, dbl, idesc, 1u);
           }
           umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+          tr.ev(4);
         }
         umma_commit(&tmem_full[acc]);
       }
@@ -268,11 +342,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
   } else if (warp == kUmmaLoadWarp) {
     // =========================== W image loader (TMA 1-D) ===========================
     if (lane == 0) {
+      Tracer tr(0);
       uint32_t it = 0;
       for (int64_t i = 0; i < my_tiles; ++i) {
         for (int atom = 0; atom < Cf::kAtoms; ++atom, ++it) {
           const int s = it % kUmmaStages;
           mbar_wait(&empty[s], ((it / kUmmaStages) & 1) ^ 1);
+          tr.ev(0);
           mbar_arrive_expect_tx(&full[s], 2 * Cf::kBBytes);
           bulk_g2s(smem + s * Cf::kStageBytes + 2 * Cf::kABytes, a.wimg + (size_t)atom * (2 * H * 32), 2 * Cf::kBBytes,
                    &full[s]);
@@ -298,11 +374,23 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
         if (row < a.n_rows) dst[u] = __ldcs(reinterpret_cast<const float4*>(z + row * H + atom * 32 + ch * 4));
       }
     };
+    // lane r of producer warp pw prefetches (L2) the 128-byte atom row r of its 32 rows
+    auto prefetch_atom = [&](int64_t it) {
+      if (it >= total || (a.dbg & 8u)) return;
+      const int64_t tile = (int64_t)blockIdx.x + (it / Cf::kAtoms) * gridDim.x;
+      const int64_t row = tile * kUmmaM + pw * 32 + lane;
+      if (row < a.n_rows) prefetch_l2(z + row * H + (int)(it % Cf::kAtoms) * 32);
+    };
+    constexpr int kAheadA = 4;
+    Tracer tr(pw == 0 && lane == 0 ? 1 : -1000000);
+    for (int it = 1; it < kAheadA; ++it) prefetch_atom(it);
     if (total > 0) load_atom(0, cur);
     for (int64_t it = 0; it < total; ++it) {
+      prefetch_atom(it + kAheadA);
       if (it + 1 < total) load_atom(it + 1, nxt);
       const int s = (int)(it % kUmmaStages);
       mbar_wait(&empty[s], (uint32_t)(((it / kUmmaStages) & 1) ^ 1));
+      tr.ev(1);
       unsigned char* a_hi = smem + s * Cf::kStageBytes;
       unsigned char* a_lo = a_hi + Cf::kABytes;
 #pragma unroll
@@ -319,6 +407,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
       fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      tr.ev(2);
 #pragma unroll
       for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
     }

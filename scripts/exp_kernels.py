@@ -18,7 +18,12 @@ import ndcn_b200 as nb  # noqa: E402
 from ndcn_b200 import _ffi, workloads as wl  # noqa: E402
 
 
+QUICK = False
+
+
 def timed(fn, reps=5, warm=2):
+    if QUICK:
+        reps, warm = 1, 0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -39,10 +44,20 @@ def main():
     ap.add_argument("--nodes", type=int, default=1_000_000)
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--graph", default="power_law")
+    ap.add_argument("--quick", action="store_true", help="one untimed pass per variant (for ncu captures)")
+    ap.add_argument("--spmm-only", action="store_true")
     args = ap.parse_args()
+    global QUICK
+    QUICK = args.quick
     dev = torch.device("cuda")
     n, H = args.nodes, args.hidden
-    a = wl.power_law_adjacency(n, 5, seed=0) if args.graph == "power_law" else wl.erdos_renyi_adjacency(n, 10.0, seed=0)
+    if args.graph == "power_law":
+        a = wl.power_law_adjacency(n, 5, seed=0)
+    elif args.graph == "grid":
+        a = wl.grid_adjacency(int(round(n ** 0.5)))
+        n = a.shape[0]
+    else:
+        a = wl.erdos_renyi_adjacency(n, 10.0, seed=0)
     phi = wl.graph_operator(a, "norm_lap")
     g = nb.CsrGraph.from_scipy(phi, dev)
     nnz = g.nnz
@@ -54,18 +69,21 @@ def main():
     gather_bytes = nnz * H * 4
 
     ref = None
-    for cw in (-1, 64, 32, 16):
-        _ffi.configure(gather_cw=cw)
+    for cw, ver in ((-1, 1), (32, 1), (32, 2), (64, 2)):
+        _ffi.configure(gather_cw=cw, gather_version=ver)
         med, best = timed(lambda: nb.spmm(g, x))
         out = nb.spmm(g, x)
         if ref is None:
             ref = out
         diff = float((out - ref).abs().max())
-        res["spmm_cw%d" % cw] = {"ms": med, "best_ms": best, "gathered_GBps": gather_bytes / med / 1e6,
+        res["spmm_cw%d_v%d" % (cw, ver)] = {"ms": med, "best_ms": best, "gathered_GBps": gather_bytes / med / 1e6,
                                  "max_abs_diff_vs_fullrow": diff}
-        print("spmm cw=%d: %.3f ms (best %.3f)  gathered %.0f GB/s  diff %.2e" %
-              (cw, med, best, gather_bytes / med / 1e6, diff), flush=True)
+        print("spmm cw=%d v%d: %.3f ms (best %.3f)  gathered %.0f GB/s  diff %.2e" %
+              (cw, ver, med, best, gather_bytes / med / 1e6, diff), flush=True)
     del ref
+    if args.spmm_only:
+        print(json.dumps(res))
+        return
 
     spec = nb.RhsSpec.ndcn(H, W, b)
     spec_ng = nb.RhsSpec.ndcn(H, W, b, no_graph=True)
@@ -83,8 +101,8 @@ def main():
     res["rhs_umma_no_graph"] = {"ms": med, "best_ms": best, "GBps_2NH": 2 * n * H * 4 / med / 1e6}
     print("rhs umma no_graph (GEMM+epilogue only): %.3f ms  (%.0f GB/s of read+write)" %
           (med, 2 * n * H * 4 / med / 1e6), flush=True)
-    for cw in (0, 32, 16):
-        _ffi.configure(stage_impl=_ffi.IMPL_UMMA, gather_cw=cw)
+    for cw in (-1, 32, 64):
+        _ffi.configure(stage_impl=_ffi.IMPL_UMMA, gather_cw=cw, gather_version=2)
         med, best = timed(lambda: nb.rhs_eval(g, spec, x))
         out = nb.rhs_eval(g, spec, x)
         d = float((out - simt).abs().max())

@@ -44,18 +44,19 @@ def _graph(n, avg_deg, seed, hub=0):
 
 @pytest.mark.parametrize("H", [64, 128, 256])
 @pytest.mark.parametrize("cw", [16, 32, 64])
-def test_chunked_gather_vs_full_row_and_torch(knobs, H, cw):
+@pytest.mark.parametrize("version", [1, 2])
+def test_chunked_gather_vs_full_row_and_torch(knobs, H, cw, version):
     """regular rows accumulate in CSR order in both kernels -> bitwise equal; rows above 256
     entries (two hubs here) are reduced by a CTA of their own -> fp32 tolerance"""
     import ndcn_b200 as nb
-    n = 4099
+    n = 4099 if version == 1 else 40961  # v2: more 128-row items than resident CTAs, a ragged last block
     Phi = _graph(n, 11, seed=cw + H, hub=1500)
     g = nb.CsrGraph.from_tensor(Phi, torch.device("cuda"))
     torch.manual_seed(H)
     x = torch.randn(n, H)
     knobs(gather_cw=-1)
     full = nb.spmm(g, x.cuda()).cpu()
-    knobs(gather_cw=cw)
+    knobs(gather_cw=cw, gather_version=version)
     chunked = nb.spmm(g, x.cuda()).cpu()
     deg = np.diff(g.rowptr.cpu().numpy())
     short = torch.from_numpy(deg <= 256)
