@@ -152,6 +152,32 @@ __device__ __forceinline__ void ldv_stream(const float* __restrict__ p, float (&
     v[0] = __ldcs(p);
   }
 }
+// 16-byte load with an explicit L2 eviction policy (createpolicy value)
+__device__ __forceinline__ void ldv4_policy(const float* __restrict__ p, float (&v)[4], uint64_t pol) {
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+template <int VW>
+__device__ __forceinline__ void stv_stream(float* __restrict__ p, const float (&v)[VW]) {
+  if constexpr (VW == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  } else if constexpr (VW == 2) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  } else {
+    __stcs(p, v[0]);
+  }
+}
 template <int VW>
 __device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[VW]) {
   if constexpr (VW == 4) {
@@ -186,10 +212,15 @@ __device__ __forceinline__ void epi_load(const EpiCtx& c, int64_t off, EpiIn<VW>
     if (j < c.n_prev) ldv_stream<VW>(c.kprev[j] + off, in.kp[j]);
 }
 
+// stream_out: k_out / y_out are written with streaming (evict-first) stores -- for states far larger
+// than L2, where a written line is gone long before the next kernel reads it
 template <int VW>
 __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const float (&k)[VW], const EpiIn<VW>& in,
-                                         double& err_acc) {
-  if (c.k_out != nullptr) stv<VW>(c.k_out + off, k);
+                                         double& err_acc, bool stream_out = false) {
+  if (c.k_out != nullptr) {
+    if (stream_out) stv_stream<VW>(c.k_out + off, k);
+    else stv<VW>(c.k_out + off, k);
+  }
   if (c.mode == EPI_STORE) return;
 
   if (c.mode == EPI_LINCOMB) {
@@ -216,7 +247,8 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
     float out[VW];
 #pragma unroll
     for (int i = 0; i < VW; ++i) out[i] = fadd(in.y0[i], acc[i]);
-    stv<VW>(c.y_out + off, out);
+    if (stream_out) stv_stream<VW>(c.y_out + off, out);
+    else stv<VW>(c.y_out + off, out);
     return;
   }
 
@@ -265,7 +297,8 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
       out[i] = fadd(in.y0[i], fmul(s, dt8));
     }
   }
-  stv<VW>(c.y_out + off, out);
+  if (stream_out) stv_stream<VW>(c.y_out + off, out);
+    else stv<VW>(c.y_out + off, out);
 }
 
 template <int VW>

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     const int half = warp >> 2;    // which half of the H columns
     float4* st4 = reinterpret_cast<float4*>(staging + warp * 32 * kUmmaStagePitch);
     const bool relu = !(a.flags & NDCN_F_NO_RELU);
+    const bool stream_out = (a.dbg & 16u) == 0 && (int64_t)a.n_rows * H * 4 > ((int64_t)256 << 20);
     const int rsub = lane >> 3;    // after the transpose: 8 lanes x 16 bytes per row, 4 rows per instruction
     const int cg = lane & 7;
     constexpr int kChunks = H / 2 / 32;
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
 #pragma unroll
                 for (int e4 = 0; e4 < 4; ++e4) kv[e4] = fmaxf(kv[e4], 0.f);
               }
-              epi_math<4>(c, row * H + c0 + 4 * cg, kv, in[u], err_acc);
+              epi_math<4>(c, row * H + c0 + 4 * cg, kv, in[u], err_acc, stream_out);
             }
           }
         }
