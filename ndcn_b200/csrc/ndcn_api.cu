@@ -39,8 +39,6 @@ struct ndcn_graph {
   int32_t* long_rows = nullptr;  // rows with more than kLongRow entries (device)
   int n_long = 0;
   int max_deg = 0;
-  int32_t* col_tagged = nullptr;  // private copy of col, bit 31 = column is one of the n_hubs most referenced
-  int n_hubs = 0;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -51,7 +49,6 @@ struct Config {
   int gather_cw = 0;                // 0 auto, -1 full-row gather, else chunk width in floats (16/32/64)
   int64_t umma_min_rows = 8192;     // auto: tcgen05 path from this many rows
   int gather_v = 2;                 // chunk-major gather flavour: 1 one row per lane group, 2 persistent + TMA-staged CSR
-  int64_t hub_rows = 40960;         // columns tagged for L2 evict_last in the full-row gather (0 = off)
 };
 static Config& cfg() {
   static Config c = [] {
@@ -60,7 +57,6 @@ static Config& cfg() {
     if (const char* v = std::getenv("NDCN_GATHER_CW")) k.gather_cw = std::atoi(v);
     if (const char* v = std::getenv("NDCN_UMMA_MIN_ROWS")) k.umma_min_rows = std::atoll(v);
     if (const char* v = std::getenv("NDCN_GATHER_V")) k.gather_v = std::atoi(v);
-    if (const char* v = std::getenv("NDCN_HUB_ROWS")) k.hub_rows = std::atoll(v);
     return k;
   }();
   return c;
@@ -170,17 +166,10 @@ static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaSt
     *grid_out = grid;
     // H=256: 4 CTAs/SM (64 registers) x 4 row loads in flight per lane measured best on B200
     // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
-    if constexpr (VW == 4 && NCH == 2) {
-      if (a.col_tagged != nullptr && n_long >= 0 && !(a.flags & NDCN_F_NO_GRAPH)) {
-        NdcnArgs a2 = a;
-        a2.g.col = a.col_tagged;
-        k_stage_ndcn_row<VW, NCH, 4, 4, true><<<grid, kStageThreads, 0, st>>>(a2, e);
-      } else {
-        k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
-      }
-    } else {
-      k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
-    }
+    // H=256: 4 CTAs/SM (64 registers) x 4 row loads in flight per lane measured best on B200
+    // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
+    if constexpr (VW == 4 && NCH == 2) k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
+    else k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
   } else {
     using S = GemmSmem<VW, NCH>;
     static bool attr_set = false;
@@ -364,7 +353,6 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
     a.flags = r.flags;
     a.long_rows = b.g->long_rows;
     a.n_long = b.g->n_long;
-    a.col_tagged = b.g->col_tagged;
     const bool need_w = !(r.flags & NDCN_F_NO_CONTROL);
     if (need_w && (r.W == nullptr || r.b == nullptr)) return NDCN_E_ARG;
     if (r.H < 1 || r.H > 1024) return NDCN_E_ARG;
@@ -502,54 +490,13 @@ extern "C" int ndcn_graph_create(int64_t n_rows, int64_t n_cols, int64_t nnz, co
       }
     }
   }
-  // hub tagging for the L2 eviction policy of the full-row gather: only worth it when the gather
-  // source cannot be L2-resident anyway (more columns than the hub budget by a wide margin)
-  const int64_t hub_budget = cfg().hub_rows;
-  if (hub_budget > 0 && n_cols > 8 * hub_budget && nnz > 0) {
-    std::vector<int32_t> hc((size_t)nnz);
-    cudaError_t ce = cudaMemcpy(hc.data(), col, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost);
-    if (ce == cudaSuccess) {
-      std::vector<int32_t> cnt((size_t)n_cols, 0);
-      bool ok = true;
-      for (int64_t i = 0; i < nnz; ++i) {
-        const int32_t c = hc[i];
-        if (c < 0 || c >= n_cols) {
-          ok = false;
-          break;
-        }
-        cnt[c] += 1;
-      }
-      if (!ok) {
-        ndcn_graph_destroy(g);
-        return NDCN_E_ARG;
-      }
-      std::vector<int32_t> sorted(cnt);
-      std::nth_element(sorted.begin(), sorted.begin() + (n_cols - hub_budget), sorted.end());
-      const int32_t thr = std::max<int32_t>(sorted[n_cols - hub_budget], 2);  // a column referenced once is no hub
-      int64_t n_tag = 0;
-      for (int64_t cidx = 0; cidx < n_cols; ++cidx) n_tag += cnt[cidx] >= thr ? 1 : 0;
-      for (int64_t i = 0; i < nnz; ++i)
-        if (cnt[hc[i]] >= thr) hc[i] |= (int32_t)0x80000000;
-      ce = cudaMalloc((void**)&g->col_tagged, sizeof(int32_t) * nnz);
-      if (ce == cudaSuccess)
-        ce = cudaMemcpy(g->col_tagged, hc.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice);
-      if (ce != cudaSuccess) {
-        ndcn_graph_destroy(g);
-        return (int)ce;
-      }
-      g->n_hubs = (int)n_tag;
-    } else {
-      ndcn_graph_destroy(g);
-      return (int)ce;
-    }
-  }
   *out = g;
   return NDCN_OK;
 }
 
 extern "C" int ndcn_graph_destroy(ndcn_graph_t* g) {
   if (g && g->long_rows) cudaFree(g->long_rows);
-  if (g && g->col_tagged) cudaFree(g->col_tagged);
+
   delete g;
   return NDCN_OK;
 }

@@ -152,22 +152,6 @@ __device__ __forceinline__ void ldv_stream(const float* __restrict__ p, float (&
     v[0] = __ldcs(p);
   }
 }
-// 16-byte load with an explicit L2 eviction policy (createpolicy value)
-__device__ __forceinline__ void ldv4_policy(const float* __restrict__ p, float (&v)[4], uint64_t pol) {
-  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-               : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
 template <int VW>
 __device__ __forceinline__ void stv_stream(float* __restrict__ p, const float (&v)[VW]) {
   if constexpr (VW == 4) {

@@ -25,34 +25,18 @@ constexpr int kKChunk = 16;     // W^T rows per TMA bulk chunk
 // ---------------------------------------------------------------------------------------
 // Entries [start, end) of one row, visited in batches of 32 starting at `start` with a stride of
 // `batch_stride` entries (32 for a whole row; 32 * n_warps when the warps of a CTA share a long row).
-//
-// HUB (VW == 4 only): `col` is the library's tagged copy of the column indices -- bit 31 marks the
-// columns with the highest in-degree (ndcn_graph_create).  Their rows are loaded with an L2
-// evict_last policy, every other row with evict_first, so that the hub rows a power-law graph
-// keeps coming back to stay L2-resident while the 1 KB rows that are touched a handful of times
-// stream through.
-template <int VW, int NCH, int U = 4, bool HUB = false>
+template <int VW, int NCH, int U = 4>
 __device__ __forceinline__ void gather_range(const GraphView& g, int start, int end, int batch_stride,
                                              const float* __restrict__ x, int lane, float (&acc)[NCH][VW]) {
   constexpr int H = 32 * VW * NCH;
-  static_assert(!HUB || VW == 4, "policy loads are 16-byte loads");
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
     for (int i = 0; i < VW; ++i) acc[ch][i] = 0.f;
   const float* xl = x + lane * VW;
-  uint64_t pol_last = 0, pol_first = 0;
-  if constexpr (HUB) {
-    pol_last = l2_policy_evict_last();
-    pol_first = l2_policy_evict_first();
-  }
-  auto load_row = [&](int ctag, float (&dst)[NCH][VW]) {
-    const int cc = ctag & 0x7fffffff;
+  auto load_row = [&](int cc, float (&dst)[NCH][VW]) {
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if constexpr (HUB) ldv4_policy(xl + (int64_t)cc * H + ch * 32 * VW, dst[ch], ctag < 0 ? pol_last : pol_first);
-      else ldv<VW>(xl + (int64_t)cc * H + ch * 32 * VW, dst[ch]);
-    }
+    for (int ch = 0; ch < NCH; ++ch) ldv<VW>(xl + (int64_t)cc * H + ch * 32 * VW, dst[ch]);
   };
   for (int base = start; base < end; base += batch_stride) {
     const int idx = base + lane;
@@ -112,7 +96,6 @@ struct NdcnArgs {
   uint32_t flags;     // NDCN_F_*
   const int32_t* long_rows;  // rows with more than kLongRow entries (may be null)
   int n_long;
-  const int32_t* col_tagged; // hub-tagged copy of g.col (bit 31), or null
 };
 
 // ---------------------------------------------------------------------------------------
@@ -123,7 +106,7 @@ struct NdcnArgs {
 // after every other row is done: rows above kLongRow entries are skipped by the row-per-warp
 // CTAs and handled by the first n_long CTAs of the grid, whose 8 warps interleave 32-entry
 // batches of the row and add their partial sums in warp order (fixed, reproducible).
-template <int VW, int NCH, int U = 4, int MINB = 3, bool HUB = false>
+template <int VW, int NCH, int U = 4, int MINB = 3>
 __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs a, EpiArgs e) {
   constexpr int H = 32 * VW * NCH;
   __shared__ float s_part[kWarpsPerCta][H];
@@ -140,7 +123,7 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs
     const int64_t row = __ldg(a.long_rows + blockIdx.x);
     const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
     float acc[NCH][VW];
-    gather_range<VW, NCH, U, HUB>(a.g, start + warp * 32, end, 32 * kWarpsPerCta, x, lane, acc);
+    gather_range<VW, NCH, U>(a.g, start + warp * 32, end, 32 * kWarpsPerCta, x, lane, acc);
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) stv<VW>(&s_part[warp][ch * 32 * VW + lane * VW], acc[ch]);
     __syncthreads();
@@ -174,7 +157,7 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs
       } else {
         const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
         if (n_long > 0 && end - start > kLongRow) mine = false;  // produced by a long-row CTA
-        else gather_range<VW, NCH, U, HUB>(a.g, start, end, 32, x, lane, acc);
+        else gather_range<VW, NCH, U>(a.g, start, end, 32, x, lane, acc);
       }
       if (mine) {
 #pragma unroll
