@@ -303,20 +303,49 @@ static int launch_gather(const RhsBinding& b, const NdcnArgs& a, int H, EpiArgs&
 }
 
 // ---- tcgen05 GEMM + epilogue ---------------------------------------------------------------
-template <int H>
-static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_out, cudaStream_t st) {
+template <int H, int MODE, int NPREV, int B>
+static int launch_umma_inst(const UmmaArgs& u, EpiArgs& e, int grid, cudaStream_t st) {
   using Cf = UmmaCfg<H>;
   static bool attr_set = false;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(k_stage_gemm_umma<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::kSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k_stage_gemm_umma<H, MODE, NPREV, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)Cf::kSmemBytes));
     attr_set = true;
   }
+  k_stage_gemm_umma<H, MODE, NPREV, B><<<grid, kUmmaThreads, Cf::kSmemBytes, st>>>(u, e);
+  return (int)cudaGetLastError();
+}
+
+// one instantiation per Runge-Kutta stage shape (epilogue mode x number of earlier stages read)
+template <int H>
+static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_out, cudaStream_t st) {
   const int64_t n_tiles = (u.n_rows + kUmmaM - 1) / kUmmaM;
   const int grid = (int)std::min<int64_t>(n_tiles, sm_count);
   *grid_out = grid;
   if (grid == 0) return 0;
-  k_stage_gemm_umma<H><<<grid, kUmmaThreads, Cf::kSmemBytes, st>>>(u, e);
-  return (int)cudaGetLastError();
+  const bool deep = ((u.dbg >> 8) & 1u) != 0;  // experiment switch: deeper epilogue batches
+#define NDCN_UMMA_CASE(MODE, NPREV, B0, B1) \
+  return deep ? launch_umma_inst<H, MODE, NPREV, B1>(u, e, grid, st) : launch_umma_inst<H, MODE, NPREV, B0>(u, e, grid, st)
+  switch (e.mode) {
+    case EPI_STORE: NDCN_UMMA_CASE(EPI_STORE, 0, 2, 4);
+    case EPI_LINCOMB:
+      switch (e.n_prev) {
+        case 0: NDCN_UMMA_CASE(EPI_LINCOMB, 0, 2, 4);
+        case 1: NDCN_UMMA_CASE(EPI_LINCOMB, 1, 2, 4);
+        case 2: NDCN_UMMA_CASE(EPI_LINCOMB, 2, 2, 4);
+        case 3: NDCN_UMMA_CASE(EPI_LINCOMB, 3, 2, 4);
+        case 4: NDCN_UMMA_CASE(EPI_LINCOMB, 4, 2, 4);
+        case 5: NDCN_UMMA_CASE(EPI_LINCOMB, 5, 2, 3);
+        default: return NDCN_E_ARG;
+      }
+    case EPI_ERR: NDCN_UMMA_CASE(EPI_ERR, 6, 2, 3);
+    case EPI_RK4_1: NDCN_UMMA_CASE(EPI_RK4_1, 0, 2, 4);
+    case EPI_RK4_2: NDCN_UMMA_CASE(EPI_RK4_2, 1, 2, 4);
+    case EPI_RK4_3: NDCN_UMMA_CASE(EPI_RK4_3, 2, 2, 4);
+    case EPI_RK4_4: NDCN_UMMA_CASE(EPI_RK4_4, 3, 2, 4);
+    default: return NDCN_E_ARG;
+  }
+#undef NDCN_UMMA_CASE
 }
 
 static bool umma_eligible(const ndcn_rhs_desc_t& r, int64_t n_rows) {

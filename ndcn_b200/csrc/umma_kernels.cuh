@@ -7,14 +7,15 @@
 // with fp32 accumulation in TMEM, which keeps the result at fp32-level accuracy (the reference
 // computes this Linear in fp32: TF32 is off by default in PyTorch).
 //
-// One persistent CTA per SM, 14 warps, warp-specialised:
+// One persistent CTA per SM, 16 warps = 4 warpgroups, warp-specialised (registers are moved from
+// the non-epilogue warpgroups to the epilogue warpgroups with setmaxnreg):
 //   warps 0-7   epilogue: tcgen05.ld (thread = row) -> +bias, ReLU -> per-warp SMEM transpose ->
 //               lane = column, coalesced 128-byte loads/stores of y0 / k_j / k_out / y_out, the
 //               loads of 8 rows are issued before any arithmetic (bytes in flight)
 //   warp  8     TMEM allocation; one elected lane issues tcgen05.mma kind::tf32, M=128, N=H, K=8
 //   warp  9     one elected lane streams the pre-split, pre-swizzled W image through SMEM with
 //               cp.async.bulk (TMA 1-D), one K-atom (32 k-values) of W_hi|W_lo per stage
-//   warps 10-13 A producers: coalesced 16-byte loads of the z tile's K-atom -> hi/lo split in
+//   warps 12-15 A producers: coalesced 16-byte loads of the z tile's K-atom -> hi/lo split in
 //               registers -> SWIZZLE_128B K-major SMEM (next atom's loads are already in flight)
 // Pipelines: full/empty mbarriers per SMEM stage (producers <-> MMA), tmem_full/tmem_empty per
 // accumulator (MMA <-> epilogue); two accumulators of H columns each, so the MMAs of tile i+1
@@ -28,13 +29,16 @@ namespace ndcn {
 constexpr int kUmmaM = 128;          // rows per tile
 constexpr int kUmmaEpiWarps = 8;
 constexpr int kUmmaMmaWarp = 8;
-constexpr int kUmmaLoadWarp = 9;
-constexpr int kUmmaProdWarp0 = 10;
+constexpr int kUmmaLoadWarp = 9;       // warps 10, 11 idle: they only return their registers
+constexpr int kUmmaProdWarp0 = 12;
 constexpr int kUmmaProdWarps = 4;
-constexpr int kUmmaThreads = 32 * (kUmmaProdWarp0 + kUmmaProdWarps);  // 448
+constexpr int kUmmaThreads = 32 * (kUmmaProdWarp0 + kUmmaProdWarps);  // 512 = 4 warpgroups
+// register budget (setmaxnreg, per warpgroup): 512 threads start at 128; the two non-epilogue
+// warpgroups drop to 88 and the two epilogue warpgroups grow to 168  (8*32*168 + 8*32*88 = 65536)
+constexpr int kUmmaRegsEpi = 168;
+constexpr int kUmmaRegsOther = 88;
 constexpr int kUmmaStages = 2;
 constexpr int kUmmaStagePitch = 32;  // floats; per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
-constexpr int kUmmaEpiBatch = 2;     // groups of 4 rows whose epilogue loads are in flight together
 
 // Optional device-side timeline of CTA 0 (ndcn_debug_umma_trace): per role a list of
 // (event << 56 | clock64) entries; profiling aid, null in production.
@@ -179,13 +183,20 @@ struct UmmaArgs {
                       // 4 prefetch lead 1 chunk instead of 2, 8 no producer prefetch
 };
 
-template <int H>
+// MODE / NPREV: the epilogue mode and the number of earlier stages it reads are compile-time
+// constants (one instantiation per Runge-Kutta stage shape): the epilogue is then straight-line code
+// with exactly NPREV + 1 loads per element group, which keeps the kernel small enough for the
+// instruction cache (a single kernel with every mode inlined four times measured 20-30 % slower).
+// kUmmaEpiBatch: groups of 4 rows whose epilogue loads are in flight together.
+template <int H, int MODE, int NPREV, int kUmmaEpiBatch>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a, EpiArgs e) {
   using Cf = UmmaCfg<H>;
   extern __shared__ __align__(1024) unsigned char smem[];
 
   EpiCtx c;
   if (!epi_resolve(e, c)) return;
+  c.mode = MODE;      // == e.mode, == the resolved n_prev: the launcher picks the instantiation
+  c.n_prev = NPREV;
   const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
   const float* __restrict__ z = sel(a.z, par);
 
@@ -228,6 +239,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
   double err_acc = 0.0;
 
   if (warp < kUmmaEpiWarps) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kUmmaRegsEpi));
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kUmmaRegsOther));
+  }
+
+  if (warp < kUmmaEpiWarps) {
     // =========================== epilogue ===========================
     const int q = warp & 3;        // TMEM lane quadrant this warp may read
     const int half = warp >> 2;    // which half of the H columns
@@ -249,7 +266,22 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
       const int64_t row = ((int64_t)blockIdx.x + ti * gridDim.x) * kUmmaM + q * 32 + lane;
       if (row < a.n_rows) epi_prefetch_l2(c, row * H + half * (H / 2) + (int)(g % kChunks) * 32, pf_bulk);
     };
-    for (int g = 0; g < kAhead; ++g) prefetch_chunk(g);
+    // experiment (dbg bit 32): tile-granular prefetch -- lane r prefetches the whole half row (all
+    // chunks, contiguous 128-byte lines) of tile ti at once, one tile ahead
+    const bool pf_tile = (a.dbg & 32u) != 0;
+    auto prefetch_tile = [&](int64_t ti) {
+      if (ti >= my_tiles) return;
+      const int64_t row = ((int64_t)blockIdx.x + ti * gridDim.x) * kUmmaM + q * 32 + lane;
+      if (row < a.n_rows) {
+#pragma unroll
+        for (int cc = 0; cc < kChunks; ++cc) epi_prefetch_l2(c, row * H + half * (H / 2) + cc * 32, false);
+      }
+    };
+    if (pf_tile) {
+      prefetch_tile(0);
+    } else {
+      for (int g = 0; g < kAhead; ++g) prefetch_chunk(g);
+    }
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
       const int acc = (int)(i & 1);
@@ -260,7 +292,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
 #pragma unroll 1
       for (int cc = 0; cc < kChunks; ++cc) {
         const int c0 = half * (H / 2) + cc * 32;
-        prefetch_chunk(i * kChunks + cc + kAhead);
+        if (!pf_tile) prefetch_chunk(i * kChunks + cc + kAhead);
+        else if (cc == 0) prefetch_tile(i + 1);
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + c0), v);
         if (cc == kChunks - 1) {
@@ -357,7 +390,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp >= kUmmaProdWarp0) {
     // =========================== A producers ===========================
     const int pw = warp - kUmmaProdWarp0;  // rows [32 pw, 32 pw + 32) of the tile
     const int rsub = lane >> 3;            // 4 rows per load instruction
@@ -417,7 +450,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
   // ---- teardown: error partial of this CTA, TMEM release ----
   tc_fence_before();
   __syncthreads();
-  if (e.mode == EPI_ERR) {
+  if (MODE == EPI_ERR) {
     double* red = reinterpret_cast<double*>(staging);  // the transpose tiles are idle now
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);

@@ -144,7 +144,15 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
             res = solver.odeint_fused(graph, spec, y0.detach().to(dev), t, method=method, rtol=float(rtol),
                                       atol=float(atol), terminal_only=terminal_only, max_num_steps=max_num_steps,
                                       **fused_kw)
-            out = res if y0.is_cuda else res.to(y0.device)
+            if y0.is_cuda:
+                out = res
+            elif y0.is_pinned():
+                # a caller that stages y0 in pinned memory gets the result the same way: one DMA instead of
+                # the pageable-destination copy (torch's caching host allocator recycles the block)
+                out = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+                out.copy_(res)
+            else:
+                out = res.to(y0.device)
     if out is None:
         require_cuda(y0.device if y0.is_cuda else None)
         if fused_kw:
