@@ -48,7 +48,7 @@ struct Config {
   int stage_impl = NDCN_IMPL_AUTO;  // which kernel family evaluates relu((Phi x) W^T + b)
   int gather_cw = 0;                // 0 auto, -1 full-row gather, else chunk width in floats (16/32/64)
   int64_t umma_min_rows = 8192;     // auto: tcgen05 path from this many rows
-  int gather_v = 2;                 // chunk-major gather flavour: 1 one row per lane group, 2 persistent + TMA-staged CSR
+  int gather_v = 1;                 // chunk-major gather flavour: 1 one row per lane group, 2 persistent + TMA-staged CSR
 };
 static Config& cfg() {
   static Config c = [] {
@@ -240,7 +240,14 @@ static int pick_gather_cw(int64_t n_cols, int H) {
   // measured on B200 (profiles/README.md, round 1): without a way to pin the [N, cw] slab in L2 the
   // chunk-major order does not beat one pass over full rows, so auto = full rows whenever the width
   // has a full-row kernel
-  if (fast_width(H)) return 0;
+  if (fast_width(H)) {
+    // mid-size states: a 32-column slab (n_cols x 128 B) that fits L2 comfortably makes the chunk-major
+    // order pay (100k nodes: 0.17 ms vs 0.45 ms, 250k: 0.49 vs 0.88 ms for H=256)
+    const double state_mb = (double)n_cols * H * 4.0 / 1048576.0;
+    const double slab_mb = (double)n_cols * 128.0 / 1048576.0;
+    if (H > 32 && state_mb > 64.0 && slab_mb <= 48.0) return 32;
+    return 0;
+  }
   const int cands[3] = {64, 32, 16};
   for (int cw : cands)
     if (H % cw == 0 && (double)n_cols * cw * 4.0 / 1048576.0 <= 72.0) return cw;
@@ -338,7 +345,12 @@ static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_ou
         case 5: NDCN_UMMA_CASE(EPI_LINCOMB, 5, 2, 3);
         default: return NDCN_E_ARG;
       }
-    case EPI_ERR: NDCN_UMMA_CASE(EPI_ERR, 6, 2, 3);
+    case EPI_ERR:
+      switch (e.n_prev) {
+        case 5: NDCN_UMMA_CASE(EPI_ERR, 5, 2, 3);
+        case 6: NDCN_UMMA_CASE(EPI_ERR, 6, 2, 3);
+        default: return NDCN_E_ARG;
+      }
     case EPI_RK4_1: NDCN_UMMA_CASE(EPI_RK4_1, 0, 2, 4);
     case EPI_RK4_2: NDCN_UMMA_CASE(EPI_RK4_2, 1, 2, 4);
     case EPI_RK4_3: NDCN_UMMA_CASE(EPI_RK4_3, 2, 2, 4);
@@ -359,11 +371,33 @@ static bool umma_eligible(const ndcn_rhs_desc_t& r, int64_t n_rows) {
 
 static EpiArgs store_only(float* out);
 
+// The reference multiplies every tableau coefficient in, zeros included (misc.py:18-25).  A term
+// (dt*0)*k_j is +-0 and leaves the fp32 running sum unchanged, so the stage that carries it can
+// skip reading k_j: dopri5's b_72 and c_err_2 are zero -> 2 of 27 state reads per step.  (Only a
+// non-finite k_j would make the product NaN, and such a k_j has already poisoned the stage inputs
+// built from it with non-zero coefficients, so the non-finite guard fires either way.)
+static void drop_zero_terms(EpiArgs& e) {
+  if (e.mode != EPI_LINCOMB && e.mode != EPI_ERR) return;
+  if (e.n_prev < 2) return;
+  int w = 0;
+  for (int j = 0; j < e.n_prev; ++j) {
+    if (e.beta[j] == 0.0f && !(w == 0 && j == e.n_prev - 1)) continue;  // keep at least one earlier term
+    e.kprev[w] = e.kprev[j];
+    e.beta[w] = e.beta[j];
+    ++w;
+  }
+  if (w == e.n_prev) return;
+  e.beta[w] = e.beta[e.n_prev];  // coefficient of the fresh k
+  for (int j = w + 1; j < 8; ++j) e.beta[j] = 0.0f;
+  e.n_prev = w;
+}
+
 // Launches f(src) fused with epilogue `e`; returns the number of per-CTA partial slots the
 // kernel writes in EPI_ERR mode through *n_partials.
 static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_partials, cudaStream_t st) {
   const ndcn_rhs_desc_t& r = *b.rhs;
   e.partials = b.partials;
+  drop_zero_terms(e);
   int grid = 0;
   int rc = 0;
   auto tick = [&](int cls) {
@@ -758,6 +792,7 @@ struct Driver : StageTimer {
 
   int epi_only(PtrPair k_in, EpiArgs e, int* n_partials = nullptr) {
     e.partials = sv->partials;
+    drop_zero_terms(e);
     const int grid = grid_for_elems(sv->numel, sv->sm_count);
     if (n_partials) *n_partials = grid;
     sv->launches += 1;

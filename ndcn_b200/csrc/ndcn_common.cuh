@@ -237,18 +237,23 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
   }
 
   if (c.mode == EPI_ERR) {
-    // err = sum_j (dt*c_err_j) k_j (7 terms, k6 fresh)           rk_common.py:60
+    // err = sum_j (dt*c_err_j) k_j (n_prev earlier stages, then the fresh one)      rk_common.py:60
     // ratio = err / (atol + rtol*max(|y0|,|y1|)); sum ratio^2      misc.py:146-157
     float acc[VW];
 #pragma unroll
     for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], in.kp[0][i]);
 #pragma unroll
     for (int j = 1; j < 6; ++j) {
+      if (j < c.n_prev) {
 #pragma unroll
-      for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], in.kp[j][i]));
+        for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[j], in.kp[j][i]));
+      }
     }
+    {
+      const float cf = c.coef_fresh;
 #pragma unroll
-    for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(c.coef[6], k[i]));
+      for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(cf, k[i]));
+    }
 #pragma unroll
     for (int i = 0; i < VW; ++i) {
       float tol = fadd(c.atol, fmul(c.rtol, fmaxf(fabsf(in.y0[i]), fabsf(in.y1[i]))));
