@@ -170,3 +170,42 @@ def test_umma_many_tiles_per_cta(knobs):
     ref_cpu = O.rhs_ndcn(Phi, W.cpu(), b.cpu(), x.cpu())[rows]
     out_relu = nb.rhs_eval(g, nb.RhsSpec.ndcn(H, W, b), x).cpu()[rows]
     torch.testing.assert_close(out_relu, ref_cpu, rtol=RTOL, atol=3e-6)
+
+
+@pytest.mark.timeout(900)
+def test_full_size_bench_workload_rhs_and_affine_solve(knobs):
+    """BASELINE.json's full size (1M-node power-law graph, H=256), default kernel selection:
+    (a) one RHS evaluation against the CPU oracle on every row (the oracle needs ~2 s for it);
+    (b) size-independent property of the whole solve: without the ReLU the system is affine, so three
+        forced dopri5 steps map an affine combination of initial states to the same combination of
+        the solutions (every kernel of the step -- gather, tcgen05 GEMM, stage epilogues, error
+        stage -- takes part)."""
+    import ndcn_b200 as nb
+    from ndcn_b200 import workloads as wl
+    n, H = 1_000_000, 256
+    phi = wl.graph_operator(wl.power_law_adjacency(n, 5, seed=0), "norm_lap")
+    g = nb.CsrGraph.from_scipy(phi, torch.device("cuda"))
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(H, H)
+    W, b = (lin.weight.detach() * 0.5), lin.bias.detach()
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(n, H, generator=gen)
+    out = nb.rhs_eval(g, nb.RhsSpec.ndcn(H, W.cuda(), b.cuda()), x.cuda()).cpu()
+    ref = O.rhs_ndcn(wl.to_reference_coo(phi), W, b, x)
+    torch.testing.assert_close(out, ref, rtol=RTOL, atol=3e-6)
+    del out, ref
+    spec = nb.RhsSpec.ndcn(H, W.cuda(), b.cuda(), relu=False)
+    t = torch.tensor([0.0, 0.125], dtype=torch.float64)
+
+    def solve(y):
+        return nb.odeint_fused(g, spec, y, t, method="dopri5", forced_dt=0.05, terminal_only=True).clone()
+
+    xa = x.cuda()
+    xb = torch.randn(n, H, generator=gen).cuda()
+    sa, sb = solve(xa), solve(xb)
+    assert _info().n_accepted == 3
+    sc = solve(0.25 * xa + 0.75 * xb)
+    comb = 0.25 * sa + 0.75 * sb
+    scale = float(comb.abs().max())
+    assert float((sc - comb).abs().max()) < 2e-5 * max(scale, 1.0)
+    assert bool(torch.isfinite(sc).all())
