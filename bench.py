@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--adaptive", action="store_true",
                     help="dopri5 with the NDCN tolerances (rtol .01, atol .001) over T=5 instead of forced steps; "
                          "reports the measured accepted/rejected steps (SURVEY.md section 8(d)); single GPU")
+    ap.add_argument("--exchange", choices=["auto", "halo", "feature"], default="auto",
+                    help="multi-GPU exchange scheme: halo rows of the row partition, feature-sharded gather, "
+                         "or whichever moves fewer bytes per RHS (auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds for the cpu_baseline sample")
@@ -276,6 +279,8 @@ def main_ours(args):
     spec = nb.RhsSpec.ndcn(H, W, b)
     x0_host = make_state(n, H, pin=True)
 
+    z_block_cols = 0
+    vols = None
     if world == 1:
         graph = nb.CsrGraph.from_scipy(phi, dev)
         exchange = None
@@ -283,7 +288,15 @@ def main_ours(args):
         part = None
     else:
         from ndcn_b200 import partition
-        part = partition.RowPartition.build(phi, world, rank, dev, H)
+        # two exchange schemes (ndcn_b200/partition.py): halo rows of a 1-D row partition, or the
+        # feature-sharded gather; take the one that moves fewer bytes per RHS on this graph
+        vols = partition.exchange_volumes(phi, world, H)
+        if args.exchange == "feature" or (args.exchange == "auto" and vols["feature"] is not None
+                                         and vols["feature"] < vols["halo"] and H in (128, 256)):
+            part = partition.FeaturePartition(phi, world, rank, dev, H)
+            z_block_cols = part.Hc
+        else:
+            part = partition.RowPartition.build(phi, world, rank, dev, H)
         graph = part.graph
         exchange = part.exchange
         x0 = x0_host[part.row0:part.row1].to(dev)
@@ -296,14 +309,14 @@ def main_ours(args):
         if args.adaptive:
             t = torch.tensor([0.0, T_TOTAL], dtype=torch.float64)
             return nb.odeint_fused(graph, spec, y0, t, method="dopri5", rtol=.01, atol=.001, terminal_only=True,
-                                   exchange=exchange, time_kernels=time_kernels, out=out)
+                                   exchange=exchange, time_kernels=time_kernels, out=out, z_block_cols=z_block_cols)
         if method == "dopri5":
             t = torch.tensor([0.0, DT * (k - 0.5)], dtype=torch.float64)  # inside the k-th step: exactly k steps
             return nb.odeint_fused(graph, spec, y0, t, method="dopri5", forced_dt=DT, terminal_only=True,
-                                   exchange=exchange, time_kernels=time_kernels, out=out)
+                                   exchange=exchange, time_kernels=time_kernels, out=out, z_block_cols=z_block_cols)
         t = torch.linspace(0, DT * k, k + 1, dtype=torch.float64)
         return nb.odeint_fused(graph, spec, y0, t, method=method, terminal_only=True, exchange=exchange,
-                               time_kernels=time_kernels, out=out)
+                               time_kernels=time_kernels, out=out, z_block_cols=z_block_cols)
 
     def barrier():
         if dist is not None:
@@ -350,7 +363,7 @@ def main_ours(args):
     gather_n = info.class_launches[_ffi.K_GATHER]
     rhs_avg_ms = (stage_ms + gather_ms) / max(stage_n, 1)
     n_rows_local = graph.n_rows
-    nnz_local = graph.nnz
+    nnz_local = graph.nnz if not z_block_cols else nnz // world  # feature-sharded: every rank gathers all rows on 1/world of the columns
     algo_bytes = bytes_rhs(n_rows_local, nnz_local, H)
     peaks = {}
     try:
@@ -441,8 +454,13 @@ def main_ours(args):
         "solver": {"nfe": info.nfe, "accepted": info.n_accepted, "rejected": info.n_rejected, "finite": finite},
     }
     if world > 1:
-        line["config"]["parallelism"] = "1-D node-row partition x%d, NCCL halo exchange before every RHS eval" % world
+        if z_block_cols:
+            line["config"]["parallelism"] = ("1-D node-row partition x%d for the state / GEMM / solver algebra, "
+                                             "feature-sharded gather: 2 NCCL all-to-alls per RHS eval" % world)
+        else:
+            line["config"]["parallelism"] = "1-D node-row partition x%d, NCCL halo exchange before every RHS eval" % world
         line["partition"] = part.describe()
+        line["partition"]["exchange_bytes_per_rhs_and_rank"] = vols
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del x0, out_buf

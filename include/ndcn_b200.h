@@ -62,8 +62,19 @@ typedef int (*ndcn_rhs_callback_t)(void* user, const float* y_dev, float* k_dev,
  *   what = 0: `buf` ([n_cols, H], first n_rows rows valid) needs its halo rows
  *             (rows n_rows..n_cols-1) filled from the owning ranks;
  *   what = 1: `buf` points at 2 doubles {sum of squared error ratios, element count}
- *             to be all-reduced (SUM) in place.                                         */
+ *             to be all-reduced (SUM) in place;
+ *   what = 2: (only with ndcn_solve_opts_t::gather_mode = NDCN_GATHER_EXTERNAL) `buf` points at a
+ *             HOST ndcn_gather_request_t: the callback must leave z = Phi * src for this rank's
+ *             rows in `z_dev`, as H / z_block_cols column blocks [n_rows, z_block_cols] stored one
+ *             after the other, enqueued on the solver's stream.  This is the feature-sharded
+ *             multi-GPU gather: all-to-all the state into column slices, gather every row of the
+ *             (replicated) graph on the local slice, all-to-all the result back.              */
 typedef int (*ndcn_exchange_callback_t)(void* user, int what, void* buf_dev);
+
+typedef struct ndcn_gather_request {
+  const float* src_dev; /* [n_rows, H] gather source, this rank's rows */
+  float* z_dev;         /* [H / z_block_cols][n_rows][z_block_cols]    */
+} ndcn_gather_request_t;
 
 typedef struct ndcn_rhs_desc {
   int32_t kind;  /* enum ndcn_rhs_kind */
@@ -100,6 +111,9 @@ enum ndcn_method { NDCN_EULER = 0, NDCN_MIDPOINT = 1, NDCN_RK4 = 2, NDCN_DOPRI5 
 
 #define NDCN_O_TERMINAL_ONLY 1u /* out holds only y(t[-1])  (ODEBlock terminal=True)      */
 #define NDCN_O_FORCED_DT 2u     /* dopri5: every step accepted, dt = forced_dt            */
+#define NDCN_GATHER_LOCAL 0    /* the library gathers Phi x itself (halo rows via exchange what=0)   */
+#define NDCN_GATHER_EXTERNAL 1 /* exchange what=2 produces z = Phi x (feature-sharded multi-GPU);
+                                  NDCN_RHS_NDCN with W, H in {128, 256} only                         */
 #define NDCN_O_TIME_KERNELS 4u  /* bracket every launch with CUDA events on `s`; per-class sums
                                    come back in ndcn_solve_stats_t (profiling aid for bench.py)   */
 
@@ -126,6 +140,8 @@ typedef struct ndcn_solve_opts {
   double first_step;           /* > 0: initial dt given, _select_initial_step skipped (dopri5.py:79-82;
                                   the reference replaces ANY user first_step by 0.01 -- the host layer
                                   reproduces that quirk, the library takes the value as given)        */
+  int32_t gather_mode;         /* NDCN_GATHER_LOCAL (0) or NDCN_GATHER_EXTERNAL */
+  int32_t z_block_cols;        /* NDCN_GATHER_EXTERNAL: column-block width of z (multiple of 32, divides H) */
 } ndcn_solve_opts_t;
 
 typedef struct ndcn_solve_stats {
@@ -175,6 +191,11 @@ int ndcn_error_ratio_f32(const float* err, const float* y0, const float* y1, dou
  * out[i, :] = x[idx[i], :], i < n_idx: packs the boundary rows another rank needs into a
  * contiguous send buffer (the reference is single-device; new with the 1-D row partition). */
 int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_idx, int32_t H, float* out,
+                       ndcn_stream_t s);
+
+/* out[q][r][c] = x[r][q*block_cols + c]: the [n_rows, H] state as H/block_cols contiguous column
+ * blocks -- the send buffer of the feature-sharded exchange (block q goes to peer q).  New.        */
+int ndcn_pack_cols_f32(const float* x, int64_t n_rows, int32_t H, int32_t block_cols, float* out,
                        ndcn_stream_t s);
 
 /* ---- library configuration -------------------------------------------------------------

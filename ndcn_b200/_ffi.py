@@ -28,6 +28,7 @@ F_NO_GRAPH, F_NO_CONTROL, F_NO_RELU = 1, 2, 4
 EULER, MIDPOINT, RK4, DOPRI5 = 0, 1, 2, 3
 METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4, "dopri5": DOPRI5}
 O_TERMINAL_ONLY, O_FORCED_DT, O_TIME_KERNELS = 1, 2, 4
+GATHER_LOCAL, GATHER_EXTERNAL = 0, 1
 K_STAGE, K_ALGEBRA, K_CONTROL, K_EMIT, K_INIT, K_GATHER = 0, 1, 2, 3, 4, 5
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
 CFG_STAGE_IMPL, CFG_GATHER_CW, CFG_UMMA_MIN_ROWS, CFG_GATHER_VERSION = 0, 1, 2, 3
@@ -48,7 +49,12 @@ class SolveOpts(C.Structure):
         ("exchange", EXCHANGE_CALLBACK), ("exchange_user", C.c_void_p),
         ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double),
         ("first_step", C.c_double),
+        ("gather_mode", C.c_int32), ("z_block_cols", C.c_int32),
     ]
+
+
+class GatherRequest(C.Structure):
+    _fields_ = [("src_dev", C.c_void_p), ("z_dev", C.c_void_p)]
 
 
 class SolveStats(C.Structure):
@@ -78,6 +84,7 @@ PROTOTYPES = {
     "ndcn_error_ratio_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int64,
                                        C.c_void_p, C.c_void_p]),
     "ndcn_pack_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ndcn_pack_cols_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_config_set": (C.c_int, [C.c_int32, C.c_int64]),
     "ndcn_config_get": (C.c_int64, [C.c_int32]),
     "ndcn_debug_umma_trace": (C.c_int, [C.c_void_p]),

@@ -226,6 +226,7 @@ struct RhsBinding {  // everything needed to launch one RHS stage
   const float* Wimg = nullptr;  // tf32 hi/lo W image (tcgen05 path)
   StageTimer* timer = nullptr;
   int64_t* launches = nullptr;
+  int z_block_cols = 0;         // > 0: Z already holds Phi x in column blocks of this width (external gather)
 };
 
 // ---- chunk-major gather ------------------------------------------------------------------
@@ -246,6 +247,10 @@ static int pick_gather_cw(int64_t n_cols, int H) {
     const double state_mb = (double)n_cols * H * 4.0 / 1048576.0;
     const double slab_mb = (double)n_cols * 128.0 / 1048576.0;
     if (H > 32 && state_mb > 64.0 && slab_mb <= 48.0) return 32;
+    // narrow states (the column slices of the feature-sharded multi-GPU gather): 8 lanes x 16 bytes per
+    // row beat the one-warp-per-row kernels whose lanes load 4 / 8 bytes (1M nodes: H=32 0.35 vs 1.17 ms,
+    // H=64 0.62 vs 0.89 ms, H=128 1.17 vs 1.33 ms)
+    if (H <= 128 && n_cols >= 4096) return 32;
     return 0;
   }
   const int cands[3] = {64, 32, 16};
@@ -420,11 +425,17 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
     if (need_w && (r.W == nullptr || r.b == nullptr)) return NDCN_E_ARG;
     if (r.H < 1 || r.H > 1024) return NDCN_E_ARG;
     const bool src_aligned = aligned16(src.p[0]) && aligned16(src.p[1]);
-    if (umma_eligible(r, a.g.n_rows) && b.Z != nullptr && b.Wimg != nullptr && src_aligned) {
+    const bool external_z = b.z_block_cols > 0;
+    if (external_z && !(umma_eligible(r, ((int64_t)1) << 40) && b.Z != nullptr && b.Wimg != nullptr)) return NDCN_E_ARG;
+    if (external_z || (umma_eligible(r, a.g.n_rows) && b.Z != nullptr && b.Wimg != nullptr && src_aligned)) {
       // (1) z = Phi x  -> Z (skipped with no_graph)   (2) k = relu(z W^T + b) + stage epilogue
       UmmaArgs u;
       u.z = src;
-      if (!(r.flags & NDCN_F_NO_GRAPH)) {
+      u.z_block_log2 = 0;
+      for (int w = external_z ? b.z_block_cols : r.H; w > 1; w >>= 1) u.z_block_log2 += 1;
+      if (external_z) {
+        u.z = pp(b.Z);  // the exchange hook has filled it (Driver::stage)
+      } else if (!(r.flags & NDCN_F_NO_GRAPH)) {
         NdcnArgs ga = a;
         ga.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
         EpiArgs se = store_only(b.Z);
@@ -777,6 +788,22 @@ struct Driver : StageTimer {
   // one RHS evaluation fused with epilogue e. `src_host` is the buffer the host knows to be the
   // source (needed for the exchange/callback hooks; the kernels themselves select by parity).
   int stage(PtrPair src, float* src_host, EpiArgs e, float* k_host, int* n_partials = nullptr) {
+    if (o->gather_mode == NDCN_GATHER_EXTERNAL) {
+      // feature-sharded multi-GPU gather: the hook turns this rank's rows of the gather source into
+      // this rank's rows of z = Phi x (two all-to-alls around a column-slice gather of the whole graph)
+      if (!o->exchange || sv->rhs.kind != NDCN_RHS_NDCN || (sv->rhs.flags & (NDCN_F_NO_GRAPH | NDCN_F_NO_CONTROL)) ||
+          !sv->Z || o->z_block_cols < 32 || sv->H % o->z_block_cols != 0)
+        return NDCN_E_ARG;
+      ndcn_gather_request_t req{src_host, sv->Z};
+      nfe += 1;
+      t_begin(NDCN_K_GATHER);
+      const int rc = o->exchange(o->exchange_user, 2, &req);
+      t_end();
+      if (rc != 0) return rc;
+      RhsBinding b2 = bind;
+      b2.z_block_cols = o->z_block_cols;
+      return launch_stage(b2, src, e, n_partials, st);
+    }
     RC_TRY(exchange(src_host));
     nfe += 1;
     if (sv->rhs.kind == NDCN_RHS_CALLBACK) {
@@ -1120,7 +1147,10 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
     sv->launches += 1;
   }
   if (sv->rhs.kind == NDCN_RHS_NDCN && fast_h && !(aligned16(out) && aligned16(y0))) return NDCN_E_ARG;
-  if (umma_eligible(sv->rhs, sv->n_rows) && sv->Wimg) {
+  if (opts->gather_mode != NDCN_GATHER_LOCAL && opts->gather_mode != NDCN_GATHER_EXTERNAL) return NDCN_E_ARG;
+  const bool external = opts->gather_mode == NDCN_GATHER_EXTERNAL;
+  if (external && !(umma_eligible(sv->rhs, ((int64_t)1) << 40) && sv->Wimg && sv->Z)) return NDCN_E_ARG;
+  if ((external || umma_eligible(sv->rhs, sv->n_rows)) && sv->Wimg) {
     if (sv->H == 256) prep_w_image<256>(sv->rhs.W, sv->Wimg, st);
     else prep_w_image<128>(sv->rhs.W, sv->Wimg, st);
     sv->launches += 1;
@@ -1206,6 +1236,17 @@ extern "C" int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_
   const int64_t blocks = (n_idx + kWarpsPerCta - 1) / kWarpsPerCta;
   const int grid = (int)std::min<int64_t>(blocks, 148 * 16);
   k_pack_rows<<<grid, kStageThreads, 0, (cudaStream_t)s>>>(x, idx, n_idx, H, out, vec);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ndcn_pack_cols_f32(const float* x, int64_t n_rows, int32_t H, int32_t block_cols, float* out,
+                                  ndcn_stream_t s) {
+  if (n_rows < 0 || H < 4 || block_cols < 4 || H % block_cols != 0 || block_cols % 4 != 0) return NDCN_E_ARG;
+  if (n_rows == 0) return NDCN_OK;
+  if (!x || !out || !aligned16(x) || !aligned16(out)) return NDCN_E_ARG;
+  const int64_t n4 = n_rows * (H / 4);
+  const int grid = (int)std::min<int64_t>((n4 + kStageThreads - 1) / kStageThreads, 148 * 16);
+  k_pack_cols<<<grid, kStageThreads, 0, (cudaStream_t)s>>>(x, n_rows, H, block_cols, out);
   return (int)cudaGetLastError();
 }
 

@@ -362,4 +362,20 @@ __global__ void k_transpose(const float* __restrict__ W, float* __restrict__ Wt,
   }
 }
 
+// out[q][r][c] = x[r][q * bc + c]: the row-sharded state as H / bc column blocks, block q being what
+// peer q gathers from (feature-sharded multi-GPU exchange).  16-byte accesses, grid-stride.
+__global__ void __launch_bounds__(kStageThreads) k_pack_cols(const float* __restrict__ x, int64_t n_rows, int H, int bc,
+                                                             float* __restrict__ out) {
+  const int h4 = H / 4, bc4 = bc / 4;
+  const int64_t n4 = n_rows * h4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t r = i / h4;
+    const int c4 = (int)(i - r * h4);
+    const int q = c4 / bc4, cc = c4 - q * bc4;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+    reinterpret_cast<float4*>(out)[((int64_t)q * n_rows + r) * bc4 + cc] = v;
+  }
+}
+
 }  // namespace ndcn

@@ -190,6 +190,10 @@ struct UmmaArgs {
   const float* bias;  // [H]
   int64_t n_rows;
   uint32_t flags;     // NDCN_F_NO_RELU
+  // z layout: plain row-major [n_rows, H] (z_block_log2 = log2 H), or column blocks
+  // [H / bc][n_rows][bc] with bc = 1 << z_block_log2 >= 32 (the feature-sharded multi-GPU gather
+  // delivers one [n_rows, H/P] block per peer and nobody has to interleave them)
+  int z_block_log2;
   uint32_t dbg;       // experiment switches (NDCN_UMMA_DBG): 1 no epilogue prefetch, 2 bulk (TMA) prefetch,
                       // 4 prefetch lead 1 chunk instead of 2, 8 no producer prefetch
 };
@@ -413,6 +417,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     const int ch = lane & 7;               // 16-byte chunk of the 128-byte atom row
     const int64_t total = my_tiles * Cf::kAtoms;
     float4 cur[8], nxt[8];
+    const int bl = a.z_block_log2;
+    const int64_t blk_stride = a.n_rows << bl;  // elements per column block
+    // first element of the 32-column K-atom `atom` of row `row`
+    auto z_atom = [&](int64_t row, int atom) -> const float* {
+      const int col0 = atom * 32;
+      return z + (int64_t)(col0 >> bl) * blk_stride + (row << bl) + (col0 & ((1 << bl) - 1));
+    };
     auto load_atom = [&](int64_t it, float4(&dst)[8]) {
       const int64_t tile = (int64_t)blockIdx.x + (it / Cf::kAtoms) * gridDim.x;
       const int atom = (int)(it % Cf::kAtoms);
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
       for (int u = 0; u < 8; ++u) {
         const int64_t row = row0 + u * 4;
         dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < a.n_rows) dst[u] = __ldcs(reinterpret_cast<const float4*>(z + row * H + atom * 32 + ch * 4));
+        if (row < a.n_rows) dst[u] = __ldcs(reinterpret_cast<const float4*>(z_atom(row, atom) + ch * 4));
       }
     };
     // lane r of producer warp pw prefetches (L2) the 128-byte atom row r of its 32 rows
@@ -430,8 +441,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
       const int64_t tile = (int64_t)blockIdx.x + (it / Cf::kAtoms) * gridDim.x;
       const int64_t row = tile * kUmmaM + pw * 32 + lane;
       if (row < a.n_rows) {
-        if (a.dbg & 128u) prefetch_l2_last(z + row * H + (int)(it % Cf::kAtoms) * 32);
-        else prefetch_l2(z + row * H + (int)(it % Cf::kAtoms) * 32);
+        if (a.dbg & 128u) prefetch_l2_last(z_atom(row, (int)(it % Cf::kAtoms)));
+        else prefetch_l2(z_atom(row, (int)(it % Cf::kAtoms)));
       }
     };
     constexpr int kAheadA = 4;

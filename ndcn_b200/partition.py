@@ -11,6 +11,16 @@ error norm needs one 2-double all-reduce per step (``what=1``).
 
 Host logic (index building) is numpy and is covered by world_size-2 gloo tests on the CPU; the
 exchange itself takes the communication backend of the default process group.
+
+``FeaturePartition`` is the second scheme, for graphs WITHOUT locality (power-law, ER): there the
+halo of a row block is nearly every remote row (0.64 GB per RHS and rank at
+N=1M, P=8), while transposing the state costs 2 (P-1)/P * 4NH/P bytes per rank (0.22 GB).  The
+state stays row-sharded for the GEMM and the solver algebra; for the gather every rank holds the
+whole graph and gathers ALL rows on its own H/P-column slice:
+    rows x all columns --all_to_all--> all rows x my columns --Phi--> --all_to_all--> rows x all columns
+The second all-to-all delivers one [n_local, H/P] block per peer; the tcgen05 stage kernel reads
+that blocked layout directly (``ndcn_solve_opts_t::z_block_cols``), so nothing is interleaved.
+``choose_partition`` picks the scheme with the smaller exchange volume.
 """
 from __future__ import annotations
 
@@ -164,8 +174,102 @@ class RowPartition:
             return _ffi.E_ARG
 
     def describe(self) -> dict:
-        return {"rows_local": self.n_local, "halo_rows": self.n_halo, "send_rows": self.n_send,
+        return {"scheme": "halo exchange", "rows_local": self.n_local, "halo_rows": self.n_halo, "send_rows": self.n_send,
                 "halo_bytes_per_rhs": self.n_halo * self.H * 4, "exchanges": self.n_exchanges}
+
+
+class FeaturePartition:
+    """Row-sharded state + feature-sharded gather (see the module docstring).  ``graph`` is the local
+    handle the solver works on (n_local rows, no entries: the solver never gathers itself),
+    ``exchange`` the hook for ``odeint_fused(..., exchange=, z_block_cols=part.Hc)``."""
+
+    def __init__(self, phi, world: int, rank: int, device: torch.device, H: int, group=None):
+        n = phi.shape[0]
+        if H % world != 0 or (H // world) % 32 != 0:
+            raise ValueError("feature-sharded gather needs H / world to be a multiple of 32 (H=%d, world=%d)" % (H, world))
+        self.world, self.rank, self.device, self.group = int(world), int(rank), device, group
+        self.H, self.Hc, self.n = int(H), int(H // world), int(n)
+        self.bounds = row_blocks(n, world)
+        self.rows = [int(self.bounds[q + 1] - self.bounds[q]) for q in range(world)]
+        self.row0, self.row1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.n_local, self.n_halo = self.rows[rank], 0
+        on_gpu = device.type == "cuda"
+        self.phi = phi.tocsr()
+        self.full_graph: Optional[CsrGraph] = CsrGraph.from_scipy(self.phi, device) if on_gpu else None
+        self.graph: Optional[CsrGraph] = None
+        if on_gpu:
+            self.graph = CsrGraph(torch.zeros(self.n_local + 1, dtype=torch.int32, device=device),
+                                  torch.zeros(0, dtype=torch.int32, device=device),
+                                  torch.zeros(0, dtype=torch.float32, device=device), self.n_local, self.n_local)
+        else:
+            import scipy.sparse as sp  # noqa: F401  (CPU branch: gloo tests of the exchange logic only)
+            c = self.phi.tocoo()
+            self._phi_cpu = torch.sparse_coo_tensor(torch.from_numpy(np.vstack((c.row, c.col)).astype(np.int64)),
+                                                    torch.from_numpy(c.data.astype(np.float32)), c.shape).coalesce()
+        self.send = torch.empty((world * self.n_local, self.Hc), dtype=torch.float32, device=device)
+        self.x_cs = torch.empty((n, self.Hc), dtype=torch.float32, device=device)
+        self.z_cs = torch.empty((n, self.Hc), dtype=torch.float32, device=device)
+        self.n_exchanges = 0
+
+    def gather(self, src: torch.Tensor, z_blocked: torch.Tensor) -> None:
+        """src [n_local, H] (this rank's rows) -> z_blocked [world * n_local, Hc]: block q holds
+        columns [q Hc, (q+1) Hc) of (Phi x)[row0:row1]."""
+        import torch.distributed as dist
+
+        P, nl, Hc = self.world, self.n_local, self.Hc
+        if src.is_cuda:
+            st = torch.cuda.current_stream(src.device).cuda_stream
+            _ffi.check(_ffi.lib().ndcn_pack_cols_f32(src.data_ptr(), nl, self.H, Hc, self.send.data_ptr(), st),
+                       "ndcn_pack_cols_f32")
+        else:
+            self.send.view(P, nl, Hc).copy_(src.view(nl, P, Hc).permute(1, 0, 2))
+        # block q of `send` (my rows, peer q's columns) -> peer q; I receive every rank's rows of MY columns,
+        # in rank order = row order: x_cs is [n, Hc] without any unpacking
+        dist.all_to_all_single(self.x_cs, self.send, output_split_sizes=self.rows, input_split_sizes=[nl] * P,
+                               group=self.group)
+        if src.is_cuda:
+            _ffi.check(_ffi.lib().ndcn_spmm_f32(self.full_graph.handle, self.x_cs.data_ptr(), self.z_cs.data_ptr(), Hc,
+                                                torch.cuda.current_stream(src.device).cuda_stream), "ndcn_spmm_f32")
+        else:
+            self.z_cs.copy_(torch.sparse.mm(self._phi_cpu, self.x_cs))
+        # rows of peer q (a contiguous block of z_cs) -> peer q; I receive one [n_local, Hc] block per peer
+        dist.all_to_all_single(z_blocked, self.z_cs, output_split_sizes=[nl] * P, input_split_sizes=self.rows,
+                               group=self.group)
+        self.n_exchanges += 1
+
+    def exchange(self, user, what: int, buf_ptr: int) -> int:
+        """``ndcn_exchange_callback_t`` (what = 1: error-norm all-reduce; what = 2: external gather)."""
+        import torch.distributed as dist
+
+        try:
+            if what == 2:
+                req = C.cast(buf_ptr, C.POINTER(_ffi.GatherRequest)).contents
+                src = _tensor_from_ptr(req.src_dev, (self.n_local, self.H), torch.float32, self.device)
+                z = _tensor_from_ptr(req.z_dev, (self.world * self.n_local, self.Hc), torch.float32, self.device)
+                self.gather(src, z)
+            elif what == 1:
+                red = _tensor_from_ptr(buf_ptr, (2,), torch.float64, self.device)
+                dist.all_reduce(red, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                raise RuntimeError("halo exchange requested from a feature-sharded partition")
+            return 0
+        except Exception as exc:  # pragma: no cover - surfaced as a status code through the C ABI
+            import traceback
+            traceback.print_exc()
+            print("ndcn_b200.partition.exchange failed:", exc)
+            return _ffi.E_ARG
+
+    def describe(self) -> dict:
+        per_rank = 2 * (self.world - 1) * self.n_local * self.Hc * 4
+        return {"scheme": "feature-sharded gather", "rows_local": self.n_local, "columns_local": self.Hc,
+                "all_to_all_bytes_per_rhs": per_rank, "exchanges": self.n_exchanges}
+
+
+def exchange_volumes(phi, world: int, H: int) -> dict:
+    """Bytes one rank receives per RHS evaluation under either scheme (rank 0's block as the sample)."""
+    blk = build_local_block(phi, world, 0)
+    return {"halo": int(blk.n_halo) * H * 4,
+            "feature": 2 * (world - 1) * blk.n_local * (H // world) * 4 if H % (32 * world) == 0 else None}
 
 
 class _DevArray:

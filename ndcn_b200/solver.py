@@ -141,13 +141,15 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
                  forced_dt: Optional[float] = None, max_num_steps: int = 0,
                  exchange: Optional[Callable] = None, out: Optional[torch.Tensor] = None,
                  time_kernels: bool = False, first_step: Optional[float] = None, safety: float = 0.0,
-                 ifactor: float = 0.0, dfactor: float = 0.0) -> torch.Tensor:
+                 ifactor: float = 0.0, dfactor: float = 0.0, z_block_cols: int = 0) -> torch.Tensor:
     """``torchdiffeq.odeint`` for a recognised RHS, entirely inside the CUDA library.
 
     y0: [n_rows, H] fp32 CUDA.  t: 1-D float tensor (any device); the values are used as
     given, promoted to float64 (callers that mirror ``ODEBlock`` round to fp32 first,
     neural_dynamics.py:71).  Returns ``[len(t), n_rows, H]`` (or ``[n_rows, H]`` if
     ``terminal_only``), and leaves counters in ``ndcn_b200.solver.last_solve_info``.
+    ``exchange`` / ``z_block_cols``: multi-GPU hooks of ``ndcn_b200.partition`` (halo exchange of a
+    1-D row partition, or the feature-sharded gather).
     """
     global last_solve_info
     if method not in _ffi.METHODS:
@@ -189,6 +191,10 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
         cb = _ffi.EXCHANGE_CALLBACK(exchange)
         keep.append(cb)
         opts.exchange = cb
+    if z_block_cols:
+        # feature-sharded multi-GPU gather (partition.FeaturePartition): the exchange hook produces Phi x
+        assert exchange is not None
+        opts.gather_mode, opts.z_block_cols = _ffi.GATHER_EXTERNAL, int(z_block_cols)
     stats = _ffi.SolveStats()
     with torch.cuda.device(dev):
         nbytes = lib.ndcn_solver_workspace_bytes(graph.n_rows, graph.n_cols, spec.H, method_id)

@@ -209,3 +209,51 @@ def test_full_size_bench_workload_rhs_and_affine_solve(knobs):
     scale = float(comb.abs().max())
     assert float((sc - comb).abs().max()) < 2e-5 * max(scale, 1.0)
     assert bool(torch.isfinite(sc).all())
+
+
+@pytest.mark.parametrize("H,bc", [(256, 32), (256, 128), (128, 64)])
+def test_external_gather_blocked_z(knobs, H, bc):
+    """NDCN_GATHER_EXTERNAL (the multi-GPU feature-sharded gather's interface) on one GPU: the exchange
+    hook produces z = Phi x in column blocks of `bc` (ndcn_pack_cols_f32), the tcgen05 kernel reads the
+    blocked layout; results must equal the library-side gather bit for bit"""
+    import ctypes as C
+    import ndcn_b200 as nb
+    from ndcn_b200 import _ffi, partition
+    n = 3000
+    Phi = _graph(n, 8, seed=H + bc)
+    g = nb.CsrGraph.from_tensor(Phi, torch.device("cuda"))
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(H, H)
+    W, b = (lin.weight.detach() * 0.5).cuda(), lin.bias.detach().cuda()
+    x = torch.randn(n, H).cuda()
+    spec = nb.RhsSpec.ndcn(H, W, b)
+    t = torch.tensor([0.0, 0.4, 1.0])
+    knobs(stage_impl=_ffi.IMPL_UMMA, gather_cw=-1)
+    ref = nb.odeint_fused(g, spec, x, t, method="dopri5", rtol=1e-3, atol=1e-4).clone()
+    ref_info = _info()
+    calls = {"gather": 0, "reduce": 0}
+    dev = torch.device("cuda")
+
+    def hook(user, what, buf_ptr):
+        if what == 2:
+            req = C.cast(buf_ptr, C.POINTER(_ffi.GatherRequest)).contents
+            src = partition._tensor_from_ptr(req.src_dev, (n, H), torch.float32, dev)
+            z = nb.spmm(g, src)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _ffi.check(_ffi.lib().ndcn_pack_cols_f32(z.data_ptr(), n, H, bc, req.z_dev, st))
+            calls["gather"] += 1
+        elif what == 1:
+            calls["reduce"] += 1  # one rank: the sums are already global
+        else:
+            return _ffi.E_ARG
+        return 0
+
+    out = nb.odeint_fused(g, spec, x, t, method="dopri5", rtol=1e-3, atol=1e-4, exchange=hook, z_block_cols=bc)
+    i = _info()
+    assert (i.nfe, i.n_accepted, i.n_rejected) == (ref_info.nfe, ref_info.n_accepted, ref_info.n_rejected)
+    assert calls["gather"] == i.nfe and calls["reduce"] > 0
+    assert torch.equal(out, ref)
+    # fixed-grid solver through the same hook
+    ref4 = nb.odeint_fused(g, spec, x, t, method="rk4").clone()
+    out4 = nb.odeint_fused(g, spec, x, t, method="rk4", exchange=hook, z_block_cols=bc)
+    assert torch.equal(out4, ref4)

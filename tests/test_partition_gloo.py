@@ -88,3 +88,55 @@ def test_single_rank_partition_is_the_whole_graph():
     blk = partition.build_local_block(phi, 1, 0)
     assert blk.n_halo == 0 and blk.n_local == 100
     assert np.array_equal(blk.col, phi.indices)
+
+
+def _feature_worker(rank, world, port, n, H, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        phi = wl.graph_operator(wl.power_law_adjacency(n, 3, seed=1), "norm_lap")
+        x = torch.from_numpy(np.random.RandomState(0).standard_normal((n, H)).astype(np.float32))
+        part = partition.FeaturePartition(phi, world, rank, torch.device("cpu"), H)
+        src = x[part.row0:part.row1].contiguous()
+        zb = torch.zeros(world * part.n_local, part.Hc)
+        part.gather(src, zb)
+        # block q = columns [q Hc, (q+1) Hc) of (Phi x)[row0:row1]
+        z = zb.view(world, part.n_local, part.Hc).permute(1, 0, 2).reshape(part.n_local, H)
+        ref = torch.from_numpy((phi @ x.numpy())[part.row0:part.row1])
+        ok = bool(torch.allclose(z, ref, rtol=1e-5, atol=1e-6))
+        # the send buffer is the column-blocked copy of this rank's rows
+        ok_send = torch.equal(part.send.view(world, part.n_local, part.Hc)[1], src[:, part.Hc:2 * part.Hc])
+        out_q.put((rank, ok, ok_send, part.describe()["all_to_all_bytes_per_rhs"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 257), (2, 64), (4, 130)])
+def test_feature_sharded_gather_gloo(world, n):
+    """all-to-all into column slices, full-graph gather on the slice, all-to-all back: the blocked
+    result must be this rank's rows of Phi x (uneven row blocks included)"""
+    H = 32 * world * 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_feature_worker, args=(r, world, port, n, H, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ok_send, nbytes in res:
+        assert ok and ok_send, (rank, ok, ok_send)
+        assert nbytes > 0
+
+
+def test_exchange_volumes_prefers_feature_sharding_without_locality():
+    phi = wl.graph_operator(wl.power_law_adjacency(20000, 5, seed=0), "norm_lap")
+    v = partition.exchange_volumes(phi, 8, 256)
+    assert v["feature"] < v["halo"]           # nearly every remote row is a halo row
+    grid = wl.graph_operator(wl.grid_adjacency(140), "norm_lap")
+    v = partition.exchange_volumes(grid, 8, 256)
+    assert v["halo"] < v["feature"]           # a grid block needs one line of nodes from each neighbour
+    assert partition.exchange_volumes(grid, 3, 256)["feature"] is None
