@@ -168,8 +168,15 @@ static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaSt
     // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
     // H=256: 4 CTAs/SM (64 registers) x 4 row loads in flight per lane measured best on B200
     // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
-    if constexpr (VW == 4 && NCH == 2) k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
-    else k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
+    if constexpr (VW == 4 && NCH == 2) {
+      k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
+    } else if constexpr (VW == 4 && NCH == 1) {
+      // H=128: 8 row loads in flight per lane at 5 CTAs/SM measured best (0.98 ms vs 1.34 ms for the
+      // default instantiation on the 1M-node power-law gather)
+      k_stage_ndcn_row<VW, NCH, 8, 5><<<grid, kStageThreads, 0, st>>>(a, e);
+    } else {
+      k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
+    }
   } else {
     using S = GemmSmem<VW, NCH>;
     static bool attr_set = false;
@@ -249,8 +256,8 @@ static int pick_gather_cw(int64_t n_cols, int H) {
     if (H > 32 && state_mb > 64.0 && slab_mb <= 48.0) return 32;
     // narrow states (the column slices of the feature-sharded multi-GPU gather): 8 lanes x 16 bytes per
     // row beat the one-warp-per-row kernels whose lanes load 4 / 8 bytes (1M nodes: H=32 0.35 vs 1.17 ms,
-    // H=64 0.62 vs 0.89 ms, H=128 1.17 vs 1.33 ms)
-    if (H <= 128 && n_cols >= 4096) return 32;
+    // H=64 0.62 vs 0.89 ms; at H=128 the tuned full-row kernel wins, 0.98 vs 1.17 ms)
+    if (H <= 64 && n_cols >= 4096) return 32;
     return 0;
   }
   const int cands[3] = {64, 32, 16};
