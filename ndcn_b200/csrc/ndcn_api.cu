@@ -342,31 +342,31 @@ static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_ou
   const int grid = (int)std::min<int64_t>(n_tiles, sm_count);
   *grid_out = grid;
   if (grid == 0) return 0;
-  const bool deep = ((u.dbg >> 8) & 1u) != 0;  // experiment switch: deeper epilogue batches
+  const bool deep = ((u.dbg >> 8) & 1u) != 0;  // experiment switch: the other epilogue batch depth
 #define NDCN_UMMA_CASE(MODE, NPREV, B0, B1) \
   return deep ? launch_umma_inst<H, MODE, NPREV, B1>(u, e, grid, st) : launch_umma_inst<H, MODE, NPREV, B0>(u, e, grid, st)
   switch (e.mode) {
-    case EPI_STORE: NDCN_UMMA_CASE(EPI_STORE, 0, 2, 4);
+    case EPI_STORE: NDCN_UMMA_CASE(EPI_STORE, 0, 2, 1);
     case EPI_LINCOMB:
       switch (e.n_prev) {
-        case 0: NDCN_UMMA_CASE(EPI_LINCOMB, 0, 2, 4);
-        case 1: NDCN_UMMA_CASE(EPI_LINCOMB, 1, 2, 4);
-        case 2: NDCN_UMMA_CASE(EPI_LINCOMB, 2, 2, 4);
-        case 3: NDCN_UMMA_CASE(EPI_LINCOMB, 3, 2, 4);
-        case 4: NDCN_UMMA_CASE(EPI_LINCOMB, 4, 2, 4);
-        case 5: NDCN_UMMA_CASE(EPI_LINCOMB, 5, 2, 3);
+        case 0: NDCN_UMMA_CASE(EPI_LINCOMB, 0, 2, 1);
+        case 1: NDCN_UMMA_CASE(EPI_LINCOMB, 1, 2, 1);
+        case 2: NDCN_UMMA_CASE(EPI_LINCOMB, 2, 2, 1);
+        case 3: NDCN_UMMA_CASE(EPI_LINCOMB, 3, 1, 2);
+        case 4: NDCN_UMMA_CASE(EPI_LINCOMB, 4, 1, 2);
+        case 5: NDCN_UMMA_CASE(EPI_LINCOMB, 5, 1, 2);
         default: return NDCN_E_ARG;
       }
     case EPI_ERR:
       switch (e.n_prev) {
-        case 5: NDCN_UMMA_CASE(EPI_ERR, 5, 2, 3);
-        case 6: NDCN_UMMA_CASE(EPI_ERR, 6, 2, 3);
+        case 5: NDCN_UMMA_CASE(EPI_ERR, 5, 1, 2);
+        case 6: NDCN_UMMA_CASE(EPI_ERR, 6, 1, 2);
         default: return NDCN_E_ARG;
       }
-    case EPI_RK4_1: NDCN_UMMA_CASE(EPI_RK4_1, 0, 2, 4);
-    case EPI_RK4_2: NDCN_UMMA_CASE(EPI_RK4_2, 1, 2, 4);
-    case EPI_RK4_3: NDCN_UMMA_CASE(EPI_RK4_3, 2, 2, 4);
-    case EPI_RK4_4: NDCN_UMMA_CASE(EPI_RK4_4, 3, 2, 4);
+    case EPI_RK4_1: NDCN_UMMA_CASE(EPI_RK4_1, 0, 2, 1);
+    case EPI_RK4_2: NDCN_UMMA_CASE(EPI_RK4_2, 1, 2, 1);
+    case EPI_RK4_3: NDCN_UMMA_CASE(EPI_RK4_3, 2, 2, 1);
+    case EPI_RK4_4: NDCN_UMMA_CASE(EPI_RK4_4, 3, 1, 2);
     default: return NDCN_E_ARG;
   }
 #undef NDCN_UMMA_CASE

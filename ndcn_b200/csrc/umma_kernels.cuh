@@ -202,7 +202,7 @@ struct UmmaArgs {
 // constants (one instantiation per Runge-Kutta stage shape): the epilogue is then straight-line code
 // with exactly NPREV + 1 loads per element group, which keeps the kernel small enough for the
 // instruction cache (a single kernel with every mode inlined four times measured 20-30 % slower).
-// kUmmaEpiBatch: groups of 4 rows whose epilogue loads are in flight together.
+// kUmmaEpiBatch (1 or 2): groups of 4 rows per load batch; two batches are in flight (software pipeline).
 template <int H, int MODE, int NPREV, int kUmmaEpiBatch>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a, EpiArgs e) {
   using Cf = UmmaCfg<H>;
@@ -314,6 +314,35 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
         const int c0 = half * (H / 2) + cc * 32;
         if (!pf_tile) prefetch_chunk(i * kChunks + cc + kAhead);
         else if (cc == 0) prefetch_tile(i + 1);
+        // the stage-algebra loads run one batch ahead of the arithmetic (two register sets): the first
+        // batch of a chunk is already in flight while the accumulators are read and transposed
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * cg);
+        auto load_batch = [&](int it0, EpiIn<4>(&in)[kUmmaEpiBatch]) {
+#pragma unroll
+          for (int u = 0; u < kUmmaEpiBatch; ++u) {
+            const int64_t row = row_base + (it0 + u) * 4 + rsub;
+            if (row < a.n_rows) epi_load<4>(c, row * H + c0 + 4 * cg, in[u]);
+          }
+        };
+        auto math_batch = [&](int it0, const EpiIn<4>(&in)[kUmmaEpiBatch]) {
+#pragma unroll
+          for (int u = 0; u < kUmmaEpiBatch; ++u) {
+            const int r = (it0 + u) * 4 + rsub;
+            const int64_t row = row_base + r;
+            if (row < a.n_rows) {
+              const float4 kk = st4[r * 8 + (cg ^ (r & 7))];
+              float kv[4] = {kk.x + b4.x, kk.y + b4.y, kk.z + b4.z, kk.w + b4.w};
+              if (relu) {
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) kv[e4] = fmaxf(kv[e4], 0.f);
+              }
+              epi_math<4>(c, row * H + c0 + 4 * cg, kv, in[u], err_acc, stream_out);
+            }
+          }
+        };
+        EpiIn<4> in_a[kUmmaEpiBatch], in_b[kUmmaEpiBatch];
+        load_batch(0, in_a);
+
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * H + c0), v);
         if (cc == kChunks - 1) {
@@ -329,29 +358,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
         // lane = (row rsub of a group of 4, columns c0 + 4 cg .. +3): 128-byte segments, 16 bytes per lane
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * cg);
 #pragma unroll 1
-        for (int it0 = 0; it0 < 8; it0 += kUmmaEpiBatch) {
-          EpiIn<4> in[kUmmaEpiBatch];
-#pragma unroll
-          for (int u = 0; u < kUmmaEpiBatch; ++u) {
-            const int64_t row = row_base + (it0 + u) * 4 + rsub;
-            if (row < a.n_rows) epi_load<4>(c, row * H + c0 + 4 * cg, in[u]);
-          }
-#pragma unroll
-          for (int u = 0; u < kUmmaEpiBatch; ++u) {
-            const int r = (it0 + u) * 4 + rsub;
-            const int64_t row = row_base + r;
-            if (row < a.n_rows) {
-              const float4 kk = st4[r * 8 + (cg ^ (r & 7))];
-              float kv[4] = {kk.x + b4.x, kk.y + b4.y, kk.z + b4.z, kk.w + b4.w};
-              if (relu) {
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) kv[e4] = fmaxf(kv[e4], 0.f);
-              }
-              epi_math<4>(c, row * H + c0 + 4 * cg, kv, in[u], err_acc, stream_out);
-            }
-          }
+        for (int it0 = 0; it0 < 8; it0 += 2 * kUmmaEpiBatch) {
+          load_batch(it0 + kUmmaEpiBatch, in_b);
+          math_batch(it0, in_a);
+          if (it0 + 2 * kUmmaEpiBatch < 8) load_batch(it0 + 2 * kUmmaEpiBatch, in_a);
+          math_batch(it0 + kUmmaEpiBatch, in_b);
         }
         __syncwarp();  // the transpose tile is rewritten by the next chunk
         tr.ev(7);
