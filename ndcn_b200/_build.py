@@ -7,7 +7,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libndcn_b200.so")
+LIB_PATH = os.environ.get("NDCN_B200_LIB") or os.path.join(PKG_DIR, "libndcn_b200.so")  # override: A/B runs of two builds
 SOURCES = ["ndcn_api.cu"]
 HEADERS = ["ndcn_common.cuh", "stage_kernels.cuh", "solver_kernels.cuh", "gather_kernels.cuh", "umma_kernels.cuh"]
 

@@ -7,15 +7,14 @@
 // with fp32 accumulation in TMEM, which keeps the result at fp32-level accuracy (the reference
 // computes this Linear in fp32: TF32 is off by default in PyTorch).
 //
-// One persistent CTA per SM, 16 warps = 4 warpgroups, warp-specialised (registers are moved from
-// the non-epilogue warpgroups to the epilogue warpgroups with setmaxnreg):
+// One persistent CTA per SM, 14 warps, warp-specialised:
 //   warps 0-7   epilogue: tcgen05.ld (thread = row) -> +bias, ReLU -> per-warp SMEM transpose ->
 //               lane = column, coalesced 128-byte loads/stores of y0 / k_j / k_out / y_out, the
 //               loads of 8 rows are issued before any arithmetic (bytes in flight)
 //   warp  8     TMEM allocation; one elected lane issues tcgen05.mma kind::tf32, M=128, N=H, K=8
 //   warp  9     one elected lane streams the pre-split, pre-swizzled W image through SMEM with
 //               cp.async.bulk (TMA 1-D), one K-atom (32 k-values) of W_hi|W_lo per stage
-//   warps 12-15 A producers: coalesced 16-byte loads of the z tile's K-atom -> hi/lo split in
+//   warps 10-13 A producers: coalesced 16-byte loads of the z tile's K-atom -> hi/lo split in
 //               registers -> SWIZZLE_128B K-major SMEM (next atom's loads are already in flight)
 // Pipelines: full/empty mbarriers per SMEM stage (producers <-> MMA), tmem_full/tmem_empty per
 // accumulator (MMA <-> epilogue); two accumulators of H columns each, so the MMAs of tile i+1
@@ -29,14 +28,13 @@ namespace ndcn {
 constexpr int kUmmaM = 128;          // rows per tile
 constexpr int kUmmaEpiWarps = 8;
 constexpr int kUmmaMmaWarp = 8;
-constexpr int kUmmaLoadWarp = 9;       // warps 10, 11 idle: they only return their registers
-constexpr int kUmmaProdWarp0 = 12;
+constexpr int kUmmaLoadWarp = 9;
+constexpr int kUmmaProdWarp0 = 10;
 constexpr int kUmmaProdWarps = 4;
-constexpr int kUmmaThreads = 32 * (kUmmaProdWarp0 + kUmmaProdWarps);  // 512 = 4 warpgroups
-// register budget (setmaxnreg, per warpgroup): 512 threads start at 128; the two non-epilogue
-// warpgroups drop to 88 and the two epilogue warpgroups grow to 168  (8*32*168 + 8*32*88 = 65536)
-constexpr int kUmmaRegsEpi = 168;
-constexpr int kUmmaRegsOther = 88;
+constexpr int kUmmaThreads = 32 * (kUmmaProdWarp0 + kUmmaProdWarps);  // 448: 128 registers per thread
+// (A setmaxnreg split -- 168 registers for the epilogue warpgroups, 88 for the rest -- was measured: the
+// epilogue gained nothing from deeper register batches and the A producers, squeezed to 88 registers,
+// slowed the operand pipeline from 2.4k to 3.7k cycles per K-atom.)
 constexpr int kUmmaStages = 2;
 constexpr int kUmmaStagePitch = 32;  // floats; per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
 
@@ -252,12 +250,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
   const uint32_t tmem = *tmem_slot;
 
   double err_acc = 0.0;
-
-  if (warp < kUmmaEpiWarps) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kUmmaRegsEpi));
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kUmmaRegsOther));
-  }
 
   if (warp < kUmmaEpiWarps) {
     // =========================== epilogue ===========================
