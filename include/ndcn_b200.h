@@ -142,6 +142,13 @@ typedef struct ndcn_solve_opts {
                                   reproduces that quirk, the library takes the value as given)        */
   int32_t gather_mode;         /* NDCN_GATHER_LOCAL (0) or NDCN_GATHER_EXTERNAL */
   int32_t z_block_cols;        /* NDCN_GATHER_EXTERNAL: column-block width of z (multiple of 32, divides H) */
+  /* fused decoder: NDCN.output_layer = Linear(H -> C) applied to every returned state
+   * (neural_dynamics.py:148,159).  With dec_classes = C in 1..8 `out` is [n_t, n_rows, C]
+   * ([n_rows, C] with NDCN_O_TERMINAL_ONLY) and the [n_t, n_rows, H] slab is never written.   */
+  const float* dec_W;          /* [C, H] row-major (nn.Linear weight), device */
+  const float* dec_b;          /* [C] device, may be NULL */
+  int32_t dec_classes;         /* 0: no decoder */
+  int32_t reserved;
 } ndcn_solve_opts_t;
 
 typedef struct ndcn_solve_stats {
@@ -172,6 +179,7 @@ int ndcn_solver_destroy(ndcn_solver_t* sv);
  *          reference's dtype round trips (ODEBlock rounds vt to fp32 first,
  *          neural_dynamics.py:71; the adaptive driver then promotes, solvers.py:28)
  *   out    [n_t, n_rows, H] (or [n_rows, H] with NDCN_O_TERMINAL_ONLY); out[0] = y0
+ *          (last dimension dec_classes instead of H when the fused decoder is on)
  * Enqueues on `s`; synchronises `s` before returning (stats are final on return).      */
 int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t,
                     float* out, const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats,

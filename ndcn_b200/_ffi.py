@@ -50,6 +50,7 @@ class SolveOpts(C.Structure):
         ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double),
         ("first_step", C.c_double),
         ("gather_mode", C.c_int32), ("z_block_cols", C.c_int32),
+        ("dec_W", C.c_void_p), ("dec_b", C.c_void_p), ("dec_classes", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

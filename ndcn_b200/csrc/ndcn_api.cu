@@ -836,6 +836,22 @@ struct Driver : StageTimer {
     return (int)cudaGetLastError();
   }
 
+  bool decoding() const { return o->dec_classes > 0; }
+  size_t out_slice_elems() const { return decoding() ? (size_t)sv->n_rows * o->dec_classes : (size_t)sv->numel; }
+  // out slice `slot` <- state y: a copy, or y W_d^T + b_d with the fused decoder (NDCN.output_layer)
+  int put_state(float* out, int64_t slot, const float* y) {
+    float* dst = out + (size_t)slot * out_slice_elems();
+    if (!decoding()) {
+      if (dst != y) CU_TRY(cudaMemcpyAsync(dst, y, sizeof(float) * (size_t)sv->numel, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
+    const int64_t blocks = (sv->n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sv->sm_count * 16));
+    sv->launches += 1;
+    k_decode_rows<<<grid, kStageThreads, 0, st>>>(y, sv->n_rows, sv->H, o->dec_W, o->dec_b, o->dec_classes, dst);
+    return (int)cudaGetLastError();
+  }
+
   int poll() {
     CU_TRY(cudaMemcpyAsync(sv->ctrl_host, sv->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -851,7 +867,7 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
   cudaStream_t st = d.st;
   const bool terminal = (d.o->flags & NDCN_O_TERMINAL_ONLY) != 0;
   const bool multi = sv->n_cols > sv->n_rows;
-  const bool in_slab = !terminal && !multi;  // the output slab doubles as state storage
+  const bool in_slab = !terminal && !multi && !d.decoding();  // the output slab doubles as state storage
   const size_t bytes = sizeof(float) * (size_t)sv->numel;
   float* cur;
   if (in_slab) {
@@ -859,7 +875,7 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
     cur = out;
   } else {
     CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
-    if (!terminal) CU_TRY(cudaMemcpyAsync(out, y0, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!terminal) RC_TRY(d.put_state(out, 0, y0));
     cur = sv->Y[0];
   }
   for (int i = 0; i + 1 < n_t; ++i) {
@@ -904,12 +920,11 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
       e.y_out = pp(nxt);
       RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[3]));
     }
-    if (!in_slab && !terminal)
-      CU_TRY(cudaMemcpyAsync(out + (size_t)(i + 1) * sv->numel, nxt, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!in_slab && !terminal) RC_TRY(d.put_state(out, i + 1, nxt));
     cur = nxt;
     sv->ctrl_host->n_accept += 1;
   }
-  if (terminal) CU_TRY(cudaMemcpyAsync(out, cur, bytes, cudaMemcpyDeviceToDevice, st));
+  if (terminal) RC_TRY(d.put_state(out, 0, cur));
   CU_TRY(cudaStreamSynchronize(st));
   sv->ctrl_host->t1 = t[n_t - 1];
   return 0;
@@ -993,7 +1008,13 @@ struct Dopri {
     RC_TRY(reduce_and_control(n_partials));
     sv->launches += 1;
     d.t_begin(NDCN_K_EMIT);
-    k_emit<<<grid_for_elems(sv->numel, sv->sm_count), kStageThreads, 0, d.st>>>(emit, d.vec_ok ? 1 : 0);
+    if (d.decoding()) {
+      const int64_t blocks = (sv->n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sv->sm_count * 16));
+      k_emit_decode<<<grid, kStageThreads, 0, d.st>>>(emit);
+    } else {
+      k_emit<<<grid_for_elems(sv->numel, sv->sm_count), kStageThreads, 0, d.st>>>(emit, d.vec_ok ? 1 : 0);
+    }
     d.t_end();
     return (int)cudaGetLastError();
   }
@@ -1060,7 +1081,7 @@ struct Dopri {
     CU_TRY(cudaStreamSynchronize(st));  // ctrl_host is reused as the poll target below
 
     CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
-    if (!terminal) CU_TRY(cudaMemcpyAsync(out, y0, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!terminal) RC_TRY(d.put_state(out, 0, y0));
 
     emit.ctrl = sv->ctrl;
     emit.t_out = sv->t_out;
@@ -1072,6 +1093,11 @@ struct Dopri {
     for (int j = 0; j < 7; ++j) emit.c_mid[j] = (float)kDpMid[j];
     emit.out = out;
     emit.numel = sv->numel;
+    emit.dec_W = d.decoding() ? d.o->dec_W : nullptr;
+    emit.dec_b = d.decoding() ? d.o->dec_b : nullptr;
+    emit.dec_C = d.decoding() ? d.o->dec_classes : 0;
+    emit.H = sv->H;
+    emit.n_rows = sv->n_rows;
 
     // f0 = func(t0, y0)     dopri5.py:78
     RC_TRY(d.stage(pp(sv->Y[0]), sv->Y[0], store_only(sv->KF[0]), sv->KF[0]));
@@ -1155,6 +1181,7 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   }
   if (sv->rhs.kind == NDCN_RHS_NDCN && fast_h && !(aligned16(out) && aligned16(y0))) return NDCN_E_ARG;
   if (opts->gather_mode != NDCN_GATHER_LOCAL && opts->gather_mode != NDCN_GATHER_EXTERNAL) return NDCN_E_ARG;
+  if (opts->dec_classes < 0 || opts->dec_classes > kDecMaxC || (opts->dec_classes > 0 && !opts->dec_W)) return NDCN_E_ARG;
   const bool external = opts->gather_mode == NDCN_GATHER_EXTERNAL;
   if (external && !(umma_eligible(sv->rhs, ((int64_t)1) << 40) && sv->Wimg && sv->Z)) return NDCN_E_ARG;
   if ((external || umma_eligible(sv->rhs, sv->n_rows)) && sv->Wimg) {
@@ -1165,7 +1192,7 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
 
   int rc = 0;
   if (n_t == 1) {
-    rc = (int)cudaMemcpyAsync(out, y0, sizeof(float) * (size_t)sv->numel, cudaMemcpyDeviceToDevice, st);
+    rc = d.put_state(out, 0, y0);
     if (!rc) rc = (int)cudaStreamSynchronize(st);
   } else if (sv->method == NDCN_DOPRI5) {
     Dopri dp(d);

@@ -121,9 +121,16 @@ struct EmitArgs {
   PtrPair y0, y1, k0, k6;  // parity-selected by Ctrl::emit_parity
   const float* k[5];       // k1..k5
   float c_mid[7];          // fp32(DPS_C_MID)
-  float* out;              // [n_out, numel] or [numel] (terminal only)
+  float* out;              // [n_out, numel] or [numel] (terminal only); with a decoder [n_out, n_rows, C] / [n_rows, C]
   int64_t numel;
+  // optional fused decoder (NDCN.output_layer, neural_dynamics.py:148,159): out = y W_d^T + b_d, C <= kDecMaxC
+  const float* dec_W;      // [C, H] row-major (nn.Linear weight) or null
+  const float* dec_b;      // [C] or null
+  int dec_C, H;
+  int64_t n_rows;
 };
+
+constexpr int kDecMaxC = 8;
 
 template <int VW>
 __device__ __forceinline__ void emit_elem(const EmitArgs& a, const float* y0p, const float* y1p, const float* k0p,
@@ -207,6 +214,101 @@ __global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
     } else {
       for (int64_t i = tid; i < a.numel; i += stride)
         emit_elem<1>(a, y0p, y1p, k0p, k6p, i, dt, lo, hi, xs, terminal_only, n_out);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Decoder-fused emission: NDCN applies output_layer = Linear(H -> C)
+// to every one of the T returned states (neural_dynamics.py:159); at N=1M, H=256, T=100 the
+// [T, N, H] slab would be 102 GB.  Here the decoder runs where the state is produced and only
+// [T, N, C] is ever written.  One warp per row, lanes stride the columns, shuffle reduction.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_store(const float (&acc)[kDecMaxC], int C, const float* dec_b, float* dst, int lane) {
+#pragma unroll
+  for (int c = 0; c < kDecMaxC; ++c) {
+    if (c < C) {
+      float v = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) dst[c] = v + (dec_b ? dec_b[c] : 0.f);
+    }
+  }
+}
+
+// out[r, :] = y[r, :] W_d^T + b_d    (slot 0 = y0, fixed-grid states, terminal states)
+__global__ void __launch_bounds__(kStageThreads) k_decode_rows(const float* __restrict__ y, int64_t n_rows, int H,
+                                                               const float* __restrict__ dec_W,
+                                                               const float* __restrict__ dec_b, int C,
+                                                               float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rows; r += n_warps) {
+    float acc[kDecMaxC];
+#pragma unroll
+    for (int c = 0; c < kDecMaxC; ++c) acc[c] = 0.f;
+    for (int col = lane; col < H; col += 32) {
+      const float v = y[r * H + col];
+#pragma unroll
+      for (int c = 0; c < kDecMaxC; ++c)
+        if (c < C) acc[c] = fmaf(v, __ldg(dec_W + c * H + col), acc[c]);
+    }
+    decode_store(acc, C, dec_b, out + r * C, lane);
+  }
+}
+
+// dense output of the pending dopri5 step, decoded: same fit/evaluate arithmetic as emit_elem<1>
+__global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
+  const volatile Ctrl* ct = a.ctrl;
+  const int lo0 = ct->emit_lo, hi0 = ct->emit_hi;
+  if (lo0 >= hi0) return;
+  const int par = ct->emit_parity;
+  const int terminal_only = ct->terminal_only, n_out = ct->n_out;
+  if (terminal_only && hi0 != n_out) return;
+  const float t0 = (float)ct->emit_t0, t1 = (float)ct->emit_t1;
+  const float dt = (float)ct->emit_dt;
+  const float* y0p = sel(a.y0, par);
+  const float* y1p = sel(a.y1, par);
+  const float* k0p = sel(a.k0, par);
+  const float* k6p = sel(a.k6, par);
+  const int lane = threadIdx.x & 31, H = a.H, C = a.dec_C;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float m2dt = fmul(-2.f, dt), p2dt = fmul(2.f, dt), p5dt = fmul(5.f, dt), m3dt = fmul(-3.f, dt),
+              m4dt = fmul(-4.f, dt);
+  for (int j = terminal_only ? n_out - 1 : lo0; j < hi0; ++j) {
+    const float t = (float)a.t_out[j];
+    const float x1 = fdiv(fsub(t, t0), fsub(t1, t0));  // interp.py:59
+    const float x2 = fmul(x1, x1), x3 = fmul(x2, x1), x4 = fmul(x3, x1);
+    float* dst_slice = terminal_only ? a.out : a.out + (int64_t)j * a.n_rows * C;
+    for (int64_t r = warp0; r < a.n_rows; r += n_warps) {
+      float acc[kDecMaxC];
+#pragma unroll
+      for (int c = 0; c < kDecMaxC; ++c) acc[c] = 0.f;
+      for (int col = lane; col < H; col += 32) {
+        const int64_t off = r * H + col;
+        const float y0 = y0p[off], y1 = y1p[off];
+        float kk[7];
+        kk[0] = k0p[off];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) kk[q + 1] = a.k[q][off];
+        kk[6] = k6p[off];
+        float s = fmul(fmul(dt, a.c_mid[0]), kk[0]);
+#pragma unroll
+        for (int q = 1; q < 7; ++q) s = fadd(s, fmul(fmul(dt, a.c_mid[q]), kk[q]));
+        const float ymid = fadd(y0, s);
+        const float f0 = kk[0], f1 = kk[6];
+        const float ca = fadd(fadd(fadd(fadd(fmul(m2dt, f0), fmul(p2dt, f1)), fmul(-8.f, y0)), fmul(-8.f, y1)), fmul(16.f, ymid));
+        const float cb = fadd(fadd(fadd(fadd(fmul(p5dt, f0), fmul(m3dt, f1)), fmul(18.f, y0)), fmul(14.f, y1)), fmul(-32.f, ymid));
+        const float cc = fadd(fadd(fadd(fadd(fmul(m4dt, f0), fmul(dt, f1)), fmul(-11.f, y0)), fmul(-5.f, y1)), fmul(16.f, ymid));
+        const float cd = fmul(dt, f0);
+        const float o = fadd(fadd(fadd(fadd(fmul(ca, x4), fmul(cb, x3)), fmul(cc, x2)), fmul(cd, x1)), fmul(y0, 1.0f));
+#pragma unroll
+        for (int c = 0; c < kDecMaxC; ++c)
+          if (c < C) acc[c] = fmaf(o, __ldg(a.dec_W + c * H + col), acc[c]);
+      }
+      decode_store(acc, C, a.dec_b, dst_slice + r * C, lane);
     }
   }
 }

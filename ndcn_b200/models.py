@@ -90,10 +90,12 @@ class ODEBlock(nn.Module):
         self.adjoint = adjoint
         self.terminal = terminal
 
-    def forward(self, vt, x):
+    def forward(self, vt, x, decoder=None):
+        """``decoder=(W, b)``: extension used by ``NDCN.forward`` -- the output Linear is applied to every
+        returned state inside the solve (no ``[T, N, H]`` slab)."""
         integration_time_vector = vt.type_as(x)  # rounds the grid to the state's dtype FIRST (:71)
         return _odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
-                           method=self.method, terminal_only=bool(self.terminal))
+                           method=self.method, terminal_only=bool(self.terminal), decoder=decoder)
 
 
 class ODEBlock2(nn.Module):
@@ -144,5 +146,10 @@ class NDCN(nn.Module):
     def forward(self, vt, x):
         if not self.no_embed:
             x = self.input_layer(x)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if x.is_cuda and not needs_grad and self.num_classes <= 8:
+            # inference: output_layer is fused into the solve's emission kernels (neural_dynamics.py:159 applies it
+            # to the whole [T, N, H] slab; here only [T, N, num_classes] is ever written)
+            return self.neural_dynamic_layer(vt, x, decoder=(self.output_layer.weight, self.output_layer.bias))
         hvx = self.neural_dynamic_layer(vt, x)
         return self.output_layer(hvx)

@@ -72,12 +72,15 @@ def _needs_grad(func, y0: torch.Tensor) -> bool:
     return False
 
 
-def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, terminal_only: bool = False):
+def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, terminal_only: bool = False,
+           decoder=None):
     """Drop-in for ``torchdiffeq.odeint`` (vendored 2019 API, odeint.py:20).
 
     ``terminal_only`` (keyword-only extension used by ``ODEBlock(terminal=True)``) returns just
     ``y(t[-1])`` without materialising the ``[T, N, H]`` slab the reference builds and discards
-    (neural_dynamics.py:79).
+    (neural_dynamics.py:79).  ``decoder=(W, b)`` (keyword-only extension used by ``NDCN.forward``)
+    applies ``Linear(H -> C)`` to every returned state; on the fused path this happens inside the
+    solve and the ``[T, N, H]`` slab is never written.
     """
     tuple_input = False
     if not torch.is_tensor(y0):
@@ -141,9 +144,12 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
             if graph.n_rows != y0.shape[0]:
                 raise RuntimeError("size mismatch: operator is %dx%d, state has %d rows" %
                                    (graph.n_rows, graph.n_cols, y0.shape[0]))
+            fuse_dec = decoder is not None and 1 <= int(decoder[0].shape[0]) <= 8
             res = solver.odeint_fused(graph, spec, y0.detach().to(dev), t, method=method, rtol=float(rtol),
                                       atol=float(atol), terminal_only=terminal_only, max_num_steps=max_num_steps,
-                                      **fused_kw)
+                                      decoder=decoder if fuse_dec else None, **fused_kw)
+            if fuse_dec:
+                decoder = None  # applied
             if y0.is_cuda:
                 out = res
             elif y0.is_pinned():
@@ -162,6 +168,8 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
         out = autograd_solver.solve(func, y0, t, float(rtol), float(atol), method, **kw)
         if terminal_only:
             out = out[-1]
+    if decoder is not None:
+        out = torch.nn.functional.linear(out, decoder[0].to(out.device), None if decoder[1] is None else decoder[1].to(out.device))
     return (out,) if tuple_input else out
 
 

@@ -141,13 +141,16 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
                  forced_dt: Optional[float] = None, max_num_steps: int = 0,
                  exchange: Optional[Callable] = None, out: Optional[torch.Tensor] = None,
                  time_kernels: bool = False, first_step: Optional[float] = None, safety: float = 0.0,
-                 ifactor: float = 0.0, dfactor: float = 0.0, z_block_cols: int = 0) -> torch.Tensor:
+                 ifactor: float = 0.0, dfactor: float = 0.0, z_block_cols: int = 0,
+                 decoder: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None) -> torch.Tensor:
     """``torchdiffeq.odeint`` for a recognised RHS, entirely inside the CUDA library.
 
     y0: [n_rows, H] fp32 CUDA.  t: 1-D float tensor (any device); the values are used as
     given, promoted to float64 (callers that mirror ``ODEBlock`` round to fp32 first,
     neural_dynamics.py:71).  Returns ``[len(t), n_rows, H]`` (or ``[n_rows, H]`` if
     ``terminal_only``), and leaves counters in ``ndcn_b200.solver.last_solve_info``.
+    ``decoder=(W_d, b_d)``: apply ``Linear(H -> C)`` (NDCN.output_layer) to every returned state inside
+    the solve; the result is ``[len(t), n_rows, C]`` and the ``[len(t), n_rows, H]`` slab is never written.
     ``exchange`` / ``z_block_cols``: multi-GPU hooks of ``ndcn_b200.partition`` (halo exchange of a
     1-D row partition, or the feature-sharded gather).
     """
@@ -173,7 +176,17 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
     method_id = _ffi.METHODS[method]
     keep: list = []
     desc = spec.to_c(keep)
-    shape = (graph.n_rows, spec.H) if terminal_only else (n_t, graph.n_rows, spec.H)
+    last = spec.H
+    dec_W = dec_b = None
+    if decoder is not None:
+        # fused NDCN.output_layer: Linear(H -> C) applied to every returned state, C <= 8
+        dec_W = decoder[0].detach().to(dev, torch.float32).contiguous()
+        dec_b = decoder[1].detach().to(dev, torch.float32).contiguous() if decoder[1] is not None else None
+        if dec_W.dim() != 2 or dec_W.shape[1] != spec.H or not (1 <= dec_W.shape[0] <= 8):
+            raise ValueError("decoder weight must be [C, %d] with 1 <= C <= 8, got %s" % (spec.H, tuple(dec_W.shape)))
+        last = int(dec_W.shape[0])
+        keep.extend([dec_W, dec_b])
+    shape = (graph.n_rows, last) if terminal_only else (n_t, graph.n_rows, last)
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=dev)
     else:
@@ -191,6 +204,9 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
         cb = _ffi.EXCHANGE_CALLBACK(exchange)
         keep.append(cb)
         opts.exchange = cb
+    if dec_W is not None:
+        opts.dec_W, opts.dec_classes = dec_W.data_ptr(), last
+        opts.dec_b = dec_b.data_ptr() if dec_b is not None else None
     if z_block_cols:
         # feature-sharded multi-GPU gather (partition.FeaturePartition): the exchange hook produces Phi x
         assert exchange is not None

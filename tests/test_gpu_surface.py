@@ -141,3 +141,53 @@ def test_generic_callable_runs_on_gpu():
     out = nb.odeint(lambda tt, y: y @ M, y0, t, rtol=1e-6, atol=1e-8, method="dopri5")
     ref = O.odeint(lambda tt, y: y @ M.cpu(), y0.cpu(), t, rtol=1e-6, atol=1e-8, method="dopri5")
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["euler", "rk4", "dopri5"])
+@pytest.mark.parametrize("H,C", [(20, 1), (64, 3), (256, 8)])
+def test_fused_decoder_matches_slab_then_linear(method, H, C):
+    """NDCN.output_layer fused into the emission kernels: [T, N, C] straight from the
+    solve must equal Linear applied to the [T, N, H] slab, for every solver family, irregular times,
+    terminal-only included"""
+    import ndcn_b200 as nb
+    n = 1500
+    rs = np.random.RandomState(H + C)
+    r, c = rs.randint(0, n, 6000), rs.randint(0, n, 6000)
+    k = r != c
+    Phi = O.normalized_laplacian_coo(np.concatenate([r[k], c[k]]), np.concatenate([c[k], r[k]]), n)
+    g = nb.CsrGraph.from_tensor(Phi, torch.device("cuda"))
+    torch.manual_seed(C)
+    lin, dec = torch.nn.Linear(H, H), torch.nn.Linear(H, C)
+    W, b = (lin.weight.detach() * 0.5).cuda(), lin.bias.detach().cuda()
+    Wd, bd = dec.weight.detach().cuda(), dec.bias.detach().cuda()
+    x = torch.randn(n, H).cuda()
+    t = torch.tensor([0.0, 0.2, 0.21, 0.7, 1.3])
+    spec = nb.RhsSpec.ndcn(H, W, b)
+    kw = dict(method=method, rtol=1e-3, atol=1e-4)
+    slab = nb.odeint_fused(g, spec, x, t, **kw)
+    ref = torch.nn.functional.linear(slab, Wd, bd)
+    out = nb.odeint_fused(g, spec, x, t, decoder=(Wd, bd), **kw)
+    assert out.shape == (5, n, C)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    last = nb.odeint_fused(g, spec, x, t, decoder=(Wd, bd), terminal_only=True, **kw)
+    torch.testing.assert_close(last, ref[-1], rtol=1e-4, atol=1e-5)
+    one = nb.odeint_fused(g, spec, x, t[:1], decoder=(Wd, None), **kw)
+    torch.testing.assert_close(one[0], torch.nn.functional.linear(x, Wd), rtol=1e-4, atol=1e-5)
+
+
+def test_ndcn_forward_inference_uses_fused_decoder(golden):
+    """the model-level call: same numbers as the reference's NDCN.forward, no [T, N, H] slab"""
+    import ndcn_b200 as nb
+    g = golden("ndcn_grid400")
+    OM = csr_to_dense(g, "OM")
+    model = nb.NDCN(1, 20, OM, 1, rtol=.01, atol=.001, method="dopri5")
+    sd = {k[3:].replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")}
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    x0, t = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    with torch.no_grad():
+        pred = model(t, x0)
+        hv = model.neural_dynamic_layer(t, model.input_layer(x0))
+        ref = model.output_layer(hv)
+    assert pred.shape == ref.shape == (t.numel(), 400, 1)
+    torch.testing.assert_close(pred, ref, rtol=1e-4, atol=1e-5)
