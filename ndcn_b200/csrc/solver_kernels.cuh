@@ -277,15 +277,26 @@ __global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float m2dt = fmul(-2.f, dt), p2dt = fmul(2.f, dt), p5dt = fmul(5.f, dt), m3dt = fmul(-3.f, dt),
               m4dt = fmul(-4.f, dt);
-  for (int j = terminal_only ? n_out - 1 : lo0; j < hi0; ++j) {
-    const float t = (float)a.t_out[j];
-    const float x1 = fdiv(fsub(t, t0), fsub(t1, t0));  // interp.py:59
-    const float x2 = fmul(x1, x1), x3 = fmul(x2, x1), x4 = fmul(x3, x1);
-    float* dst_slice = terminal_only ? a.out : a.out + (int64_t)j * a.n_rows * C;
-    for (int64_t r = warp0; r < a.n_rows; r += n_warps) {
-      float acc[kDecMaxC];
+  // outputs in groups of kJB: the nine streams of the step are read once per group, not once per output
+  constexpr int kJB = 4;
+  for (int j0 = terminal_only ? n_out - 1 : lo0; j0 < hi0; j0 += kJB) {
+    const int nj = min(kJB, hi0 - j0);
+    float xp[kJB][4];
 #pragma unroll
-      for (int c = 0; c < kDecMaxC; ++c) acc[c] = 0.f;
+    for (int jj = 0; jj < kJB; ++jj) {
+      const float t = (float)a.t_out[min(j0 + jj, hi0 - 1)];
+      const float x1 = fdiv(fsub(t, t0), fsub(t1, t0));  // interp.py:59
+      xp[jj][0] = x1;
+      xp[jj][1] = fmul(x1, x1);
+      xp[jj][2] = fmul(xp[jj][1], x1);
+      xp[jj][3] = fmul(xp[jj][2], x1);
+    }
+    for (int64_t r = warp0; r < a.n_rows; r += n_warps) {
+      float acc[kJB][kDecMaxC];
+#pragma unroll
+      for (int jj = 0; jj < kJB; ++jj)
+#pragma unroll
+        for (int c = 0; c < kDecMaxC; ++c) acc[jj][c] = 0.f;
       for (int col = lane; col < H; col += 32) {
         const int64_t off = r * H + col;
         const float y0 = y0p[off], y1 = y1p[off];
@@ -303,12 +314,27 @@ __global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
         const float cb = fadd(fadd(fadd(fadd(fmul(p5dt, f0), fmul(m3dt, f1)), fmul(18.f, y0)), fmul(14.f, y1)), fmul(-32.f, ymid));
         const float cc = fadd(fadd(fadd(fadd(fmul(m4dt, f0), fmul(dt, f1)), fmul(-11.f, y0)), fmul(-5.f, y1)), fmul(16.f, ymid));
         const float cd = fmul(dt, f0);
-        const float o = fadd(fadd(fadd(fadd(fmul(ca, x4), fmul(cb, x3)), fmul(cc, x2)), fmul(cd, x1)), fmul(y0, 1.0f));
+        float wd[kDecMaxC];
 #pragma unroll
-        for (int c = 0; c < kDecMaxC; ++c)
-          if (c < C) acc[c] = fmaf(o, __ldg(a.dec_W + c * H + col), acc[c]);
+        for (int c = 0; c < kDecMaxC; ++c) wd[c] = c < C ? __ldg(a.dec_W + c * H + col) : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < kJB; ++jj) {
+          if (jj < nj) {
+            const float o = fadd(fadd(fadd(fadd(fmul(ca, xp[jj][3]), fmul(cb, xp[jj][2])), fmul(cc, xp[jj][1])),
+                                      fmul(cd, xp[jj][0])), fmul(y0, 1.0f));
+#pragma unroll
+            for (int c = 0; c < kDecMaxC; ++c)
+              if (c < C) acc[jj][c] = fmaf(o, wd[c], acc[jj][c]);
+          }
+        }
       }
-      decode_store(acc, C, a.dec_b, dst_slice + r * C, lane);
+#pragma unroll
+      for (int jj = 0; jj < kJB; ++jj) {
+        if (jj < nj) {
+          float* dst_slice = terminal_only ? a.out : a.out + (int64_t)(j0 + jj) * a.n_rows * C;
+          decode_store(acc[jj], C, a.dec_b, dst_slice + r * C, lane);
+        }
+      }
     }
   }
 }
