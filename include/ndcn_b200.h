@@ -106,6 +106,16 @@ int ndcn_spmm_f32(const ndcn_graph_t* g, const float* x, float* y, int32_t H, nd
 int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x,
                       float* out, ndcn_stream_t s);
 
+/* vjp of one ODEFunc evaluation k = relu((Phi x) W^T + b): what autograd computes through
+ * neural_dynamics.py:20-39 for the cotangent gk of k (training loops: heat_dynamics.py:333).
+ *   gp = scale * gk where k > 0, else 0                 [n, H]  (dW = gp^T z, db = column sums of gp)
+ *   z  = Phi x                                          [n, H]  (not written with NDCN_F_NO_GRAPH: z = x)
+ *   gx = Phi^T (gp W)    or gx += ... with accumulate   [n, H]
+ * g_t is the handle of Phi^T (pass g again for a symmetric operator).  Single-GPU graphs.        */
+int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, const ndcn_rhs_desc_t* rhs,
+                     const float* x, const float* gk, float scale, float* gx, int32_t accumulate,
+                     float* gp, float* z, ndcn_stream_t s);
+
 /* ---- solver -------------------------------------------------------------------------- */
 enum ndcn_method { NDCN_EULER = 0, NDCN_MIDPOINT = 1, NDCN_RK4 = 2, NDCN_DOPRI5 = 3 };
 

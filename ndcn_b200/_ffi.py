@@ -74,6 +74,8 @@ PROTOTYPES = {
     "ndcn_graph_destroy": (C.c_int, [C.c_void_p]),
     "ndcn_spmm_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ndcn_rhs_eval_f32": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ndcn_rhs_vjp_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RhsDesc), C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ndcn_solver_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "ndcn_solver_create": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_int32, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_void_p)]),

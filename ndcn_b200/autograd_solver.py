@@ -185,3 +185,118 @@ def solve(func: Callable, y0: torch.Tensor, t: torch.Tensor, rtol: float, atol: 
             n += 1
         outs.append(_dense_eval(cs, lo, hi, t[i]))
     return torch.stack(outs)
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused training path for the fixed-grid solvers (first cut).
+#
+# The dynamics scripts train NDCN with `--method euler` by default (heat_dynamics.py:22,317-334):
+# forward = the fused solver (one launch per RHS evaluation), backward = the discrete adjoint of the
+# same scheme with every RHS vjp on the library's kernels (`ndcn_rhs_vjp_f32`: gather, GEMM with a
+# ReLU-mask epilogue, GEMM with W untransposed, gather with Phi^T fused with the adjoint update).
+# For a fixed grid the discrete adjoint IS what autograd computes through torchdiffeq's loop
+# (solvers.py:79-99), up to fp32 summation order.  dW = gp^T z and db = sum gp are plain library
+# GEMM / reduction calls.  dopri5 keeps the op-by-op autograd path above: its step-size controller is
+# part of the reference's autograd graph (misc.py:160-170), which a hand-written adjoint would drop.
+# ------------------------------------------------------------------------------------------------
+def _vjp(graph: CsrGraph, graph_t: CsrGraph, spec, x, gk, scale: float, gx, accumulate: bool):
+    """(gp, z): gx (+)= d<gk*scale, f(x)>/dx;  dW = gp^T z, db = gp.sum(0) are left to the caller."""
+    import ctypes as C
+
+    from . import _ffi
+
+    gp = torch.empty_like(x)
+    z = torch.empty_like(x) if not (spec.flags & _ffi.F_NO_GRAPH) else x
+    keep: list = []
+    desc = spec.to_c(keep)
+    with torch.cuda.device(x.device):
+        rc = _ffi.lib().ndcn_rhs_vjp_f32(graph.handle, graph_t.handle, C.byref(desc), x.data_ptr(), gk.data_ptr(),
+                                         float(scale), gx.data_ptr(), 1 if accumulate else 0, gp.data_ptr(),
+                                         z.data_ptr() if z is not x else None,
+                                         _solver.current_stream_ptr(x.device))
+    _ffi.check(rc, "ndcn_rhs_vjp_f32")
+    return gp, z
+
+
+class FusedFixedGridFn(torch.autograd.Function):
+    """``odeint`` for euler | midpoint | rk4 on a recognised ODEFunc, differentiable in (y0, W, b)."""
+
+    @staticmethod
+    def forward(ctx, y0, W, b, t32, graph, graph_t, flags, method):
+        from . import _ffi
+
+        H = y0.shape[1]
+        no_control = bool(flags & _ffi.F_NO_CONTROL)
+        spec = _solver.RhsSpec(_ffi.RHS_NDCN, H, flags, None if no_control else W, None if no_control else b)
+        with torch.no_grad():
+            slab = _solver.odeint_fused(graph, spec, y0.contiguous(), t32, method=method)
+        ctx.save_for_backward(slab, W, b, t32)
+        ctx.graph, ctx.graph_t, ctx.flags, ctx.method = graph, graph_t, flags, method
+        return slab
+
+    @staticmethod
+    def backward(ctx, g_slab):
+        from . import _ffi
+
+        slab, W, b, t32 = ctx.saved_tensors
+        graph, graph_t, flags, method = ctx.graph, ctx.graph_t, ctx.flags, ctx.method
+        H = slab.shape[2]
+        no_control = bool(flags & _ffi.F_NO_CONTROL)
+        spec = _solver.RhsSpec(_ffi.RHS_NDCN, H, flags, None if no_control else W, None if no_control else b)
+        g_slab = g_slab.contiguous()
+        dW = torch.zeros_like(W) if not no_control else None
+        db = torch.zeros_like(b) if not no_control else None
+        tt = t32.detach().to("cpu", torch.float32)
+        lam = g_slab[-1].clone()
+
+        def f(x):
+            return _solver.rhs_eval(graph, spec, x)
+
+        def vjp(x, gk, scale, gx, accumulate=True):
+            gp, z = _vjp(graph, graph_t, spec, x, gk, scale, gx, accumulate)
+            if not no_control:
+                dW.addmm_(gp.t(), z)
+                db.add_(gp.sum(0))
+
+        for i in range(slab.shape[0] - 2, -1, -1):
+            y = slab[i]
+            dt = float(tt[i + 1] - tt[i])  # fp32 difference of the fp32 grid (solvers.py:81,89)
+            if method == "euler":  # y' = y + dt f(y)
+                vjp(y, lam, dt, lam)
+            elif method == "midpoint":  # y' = y + dt f(y + dt/2 f(y))
+                ym = y + f(y) * (dt / 2)
+                gm = torch.zeros_like(lam)
+                vjp(ym, lam, dt, gm, accumulate=False)      # gm = dL/dym
+                lam.add_(gm)
+                vjp(y, gm, dt / 2, lam)
+            else:  # rk4 = 3/8 rule, rk_common.py:72-78
+                k1 = f(y)
+                y2 = y + k1 * (dt / 3)
+                k2 = f(y2)
+                y3 = y + (k2 - k1 / 3) * dt
+                k3 = f(y3)
+                y4 = y + (k1 - k2 + k3) * dt
+                g4 = torch.empty_like(lam)
+                vjp(y4, lam, dt / 8, g4, accumulate=False)          # g4 = dL/dy4 via k4
+                gk3 = lam * (3 * dt / 8) + g4 * dt
+                g3 = torch.empty_like(lam)
+                vjp(y3, gk3, 1.0, g3, accumulate=False)
+                gk2 = lam * (3 * dt / 8) - g4 * dt + g3 * dt
+                g2 = torch.empty_like(lam)
+                vjp(y2, gk2, 1.0, g2, accumulate=False)
+                gk1 = lam * (dt / 8) + g4 * dt - g3 * (dt / 3) + g2 * (dt / 3)
+                lam.add_(g4).add_(g3).add_(g2)
+                vjp(y, gk1, 1.0, lam)
+            lam.add_(g_slab[i])
+        return lam, dW, db, None, None, None, None, None
+
+
+def solve_fixed_grid_fused(odefunc, y0: torch.Tensor, t: torch.Tensor, method: str, graph: CsrGraph, flags: int):
+    """Entry used by ``odeint`` when gradients are required, the RHS is a recognised ODEFunc without
+    active dropout and the method is euler | midpoint | rk4."""
+    _require_cuda_state(y0)
+    t32 = t.detach().to(torch.float32)
+    no_graph = bool(flags & 1)
+    graph_t = graph if no_graph else graph.transpose()
+    W, b = odefunc.wt.weight, odefunc.wt.bias
+    return FusedFixedGridFn.apply(y0, W, b, t32, graph, graph_t, flags, method)

@@ -115,6 +115,21 @@ static const double kDpMid[7] = {
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool; with the
+// default release threshold of 0 the pool hands its memory back to the OS at every synchronisation
+// and the next allocation pays for a fresh mapping (~100 us).  Keep freed scratch in the pool.
+static void keep_scratch_pooled() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = 1ull << 30;  // up to 1 GiB of idle scratch stays mapped
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 static inline PtrPair pp(float* a) { return PtrPair{{a, a}}; }
 static inline PtrPair pp(float* a, float* b) { return PtrPair{{a, b}}; }
@@ -367,6 +382,7 @@ static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_ou
     case EPI_RK4_2: NDCN_UMMA_CASE(EPI_RK4_2, 1, 2, 1);
     case EPI_RK4_3: NDCN_UMMA_CASE(EPI_RK4_3, 2, 2, 1);
     case EPI_RK4_4: NDCN_UMMA_CASE(EPI_RK4_4, 3, 1, 2);
+    case EPI_MASK: NDCN_UMMA_CASE(EPI_MASK, 0, 2, 1);
     default: return NDCN_E_ARG;
   }
 #undef NDCN_UMMA_CASE
@@ -601,6 +617,7 @@ static void prep_w_image(const float* W, float* img, cudaStream_t st) {
 extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x, float* out,
                                  ndcn_stream_t s) {
   if (!g || !rhs || !x || !out) return NDCN_E_ARG;
+  keep_scratch_pooled();
   cudaStream_t st = (cudaStream_t)s;
   float* Wt = nullptr;
   float* Z = nullptr;
@@ -635,6 +652,135 @@ extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* r
   if (Wt) cudaFreeAsync(Wt, st);
   if (Z) cudaFreeAsync(Z, st);
   if (Wimg) cudaFreeAsync(Wimg, st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// vjp of one RHS evaluation: what autograd computes for
+// ODEFunc.forward (neural_dynamics.py:20-39) given the cotangent of its output, on the same kernels
+// as the forward pass -- gather, (tcgen05 or FP32-FMA) GEMM with a ReLU-mask epilogue, GEMM with W
+// untransposed, gather with Phi^T fused with the accumulation into the running adjoint.
+// ---------------------------------------------------------------------------------------
+extern "C" int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, const ndcn_rhs_desc_t* rhs,
+                                const float* x, const float* gk, float scale, float* gx, int32_t accumulate,
+                                float* gp, float* z, ndcn_stream_t s) {
+  if (!g || !g_t || !rhs || !x || !gk || !gx || !gp) return NDCN_E_ARG;
+  if (rhs->kind != NDCN_RHS_NDCN || rhs->H < 1 || rhs->H > 1024) return NDCN_E_ARG;
+  keep_scratch_pooled();
+  const int H = rhs->H;
+  const int64_t n = g->v.n_rows;
+  if (g->v.n_cols != n || g_t->v.n_rows != n || g_t->v.n_cols != n) return NDCN_E_ARG;  // single-GPU graphs
+  const bool no_graph = (rhs->flags & NDCN_F_NO_GRAPH) != 0, no_control = (rhs->flags & NDCN_F_NO_CONTROL) != 0;
+  if (!no_graph && !z) return NDCN_E_ARG;
+  if (!no_control && (!rhs->W || !rhs->b)) return NDCN_E_ARG;
+  if (n == 0) return NDCN_OK;
+  cudaStream_t st = (cudaStream_t)s;
+  int sm_count = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t numel = n * H;
+  const bool vec = aligned16(x) && aligned16(gk) && aligned16(gx) && aligned16(gp) && (!z || aligned16(z)) && H % 4 == 0;
+  auto elementwise = [&](const float* k_in, EpiArgs e) {
+    k_epi_only<<<grid_for_elems(numel, sm_count), kStageThreads, 0, st>>>(pp(const_cast<float*>(k_in)), numel, e, vec ? 1 : 0);
+    return (int)cudaGetLastError();
+  };
+  auto blank = [] {
+    EpiArgs e;
+    std::memset(&e, 0, sizeof(e));
+    e.dt_src = DT_HOST;
+    return e;
+  };
+  // (a) z = Phi x
+  const float* zin = x;
+  if (!no_graph) {
+    ndcn_rhs_desc_t rg = *rhs;
+    rg.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+    RhsBinding bg{g, &rg, nullptr, nullptr, 0, sm_count};
+    RC_TRY(launch_stage(bg, pp(const_cast<float*>(x)), store_only(z), nullptr, st));
+    zin = z;
+  }
+  // (b) gp = scale * gk where relu'(.) = 1
+  EpiArgs em = blank();
+  em.mode = EPI_MASK;
+  em.dt_host = scale;
+  em.beta[0] = 1.0f;
+  em.y0 = pp(const_cast<float*>(gk));
+  em.y_out = pp(gp);
+  float* u = gp;          // no_control: the masked cotangent is what goes through Phi^T
+  float* scratch = nullptr;  // [n,H] u | [H,H] W^T | [H] zeros | two W images
+  if (no_control) {
+    RC_TRY(elementwise(zin, em));
+  } else {
+    const bool use_umma = umma_eligible(*rhs, n) && vec;
+    const size_t img = use_umma ? align_up(sizeof(float) * 2 * (size_t)H * H, 1024) : 0;
+    const size_t bytes = align_up(sizeof(float) * (size_t)numel, 1024) + align_up(sizeof(float) * (size_t)H * H, 1024) +
+                         align_up(sizeof(float) * (size_t)H, 1024) + 2 * img + 1024;
+    CU_TRY(cudaMallocAsync((void**)&scratch, bytes, st));
+    unsigned char* p = (unsigned char*)align_up((size_t)scratch, 1024);
+    u = (float*)p;
+    p += align_up(sizeof(float) * (size_t)numel, 1024);
+    float* Wt = (float*)p;
+    p += align_up(sizeof(float) * (size_t)H * H, 1024);
+    float* zeros = (float*)p;
+    p += align_up(sizeof(float) * (size_t)H, 1024);
+    float* img_fwd = use_umma ? (float*)p : nullptr;
+    float* img_bwd = use_umma ? (float*)(p + img) : nullptr;
+    k_transpose<<<(H * H + 255) / 256, 256, 0, st>>>(rhs->W, Wt, H);
+    CU_TRY(cudaMemsetAsync(zeros, 0, sizeof(float) * H, st));
+    if (use_umma) {
+      if (H == 256) {
+        prep_w_image<256>(rhs->W, img_fwd, st);
+        prep_w_image<256>(Wt, img_bwd, st);
+      } else {
+        prep_w_image<128>(rhs->W, img_fwd, st);
+        prep_w_image<128>(Wt, img_bwd, st);
+      }
+    }
+    // pre-activation mask: the forward GEMM on z with the mask epilogue
+    ndcn_rhs_desc_t rf = *rhs;
+    rf.flags = NDCN_F_NO_GRAPH;
+    RhsBinding bf{g, &rf, Wt, nullptr, 0, sm_count};
+    bf.Z = use_umma ? u : nullptr;  // non-null tag: no_graph needs no Z
+    bf.Wimg = img_fwd;
+    int rc = launch_stage(bf, pp(const_cast<float*>(zin)), em, nullptr, st);
+    // u = gp W: the same GEMM kernels with W^T in the role of W, no bias, no ReLU
+    if (rc == 0) {
+      ndcn_rhs_desc_t rb = *rhs;
+      rb.flags = NDCN_F_NO_GRAPH | NDCN_F_NO_RELU;
+      rb.W = Wt;
+      rb.b = zeros;
+      RhsBinding bb{g, &rb, rhs->W /* (W^T)^T */, nullptr, 0, sm_count};
+      bb.Z = use_umma ? u : nullptr;
+      bb.Wimg = img_bwd;
+      rc = launch_stage(bb, pp(gp), store_only(u), nullptr, st);
+    }
+    if (rc != 0) {
+      cudaFreeAsync(scratch, st);
+      return rc;
+    }
+  }
+  // (c) gx (+)= Phi^T u
+  EpiArgs eo = accumulate ? blank() : store_only(gx);
+  if (accumulate) {
+    eo.mode = EPI_LINCOMB;
+    eo.n_prev = 0;
+    eo.dt_host = 1.0f;
+    eo.beta[0] = 1.0f;
+    eo.y0 = pp(gx);
+    eo.y_out = pp(gx);
+  }
+  int rc = 0;
+  if (no_graph) {
+    rc = elementwise(u, eo);
+  } else {
+    ndcn_rhs_desc_t rt = *rhs;
+    rt.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+    RhsBinding bt{g_t, &rt, nullptr, nullptr, 0, sm_count};
+    rc = launch_stage(bt, pp(u), eo, nullptr, st);
+  }
+  if (scratch) cudaFreeAsync(scratch, st);
   return rc;
 }
 

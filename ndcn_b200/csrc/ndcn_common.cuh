@@ -51,6 +51,7 @@ enum EpiMode : int {
   EPI_RK4_2 = 4,    // y + dt*(k1/-3 + k2)                        (rk_common.py:76)
   EPI_RK4_3 = 5,    // y + dt*(k1 - k2 + k3)                      (rk_common.py:77)
   EPI_RK4_4 = 6,    // y + (k1 + 3k2 + 3k3 + k4)*(dt/8)           (rk_common.py:78, solvers.py:91)
+  EPI_MASK = 7,     // backward of the ReLU: y_out = k > 0 ? (dt*beta_0) * aux : 0, aux read through y0
 };
 
 enum DtSrc : int { DT_HOST = 0, DT_CTRL = 1, DT_CTRL_H0 = 2 };
@@ -112,6 +113,7 @@ __device__ __forceinline__ bool epi_resolve(const EpiArgs& a, EpiCtx& c) {
   else if (a.mode == EPI_RK4_2) c.n_prev = 1;
   else if (a.mode == EPI_RK4_3) c.n_prev = 2;
   else if (a.mode == EPI_RK4_4) c.n_prev = 3;
+  else if (a.mode == EPI_MASK) c.n_prev = 0;
   c.k_out = sel(a.k_out, par);
   c.y_out = sel(a.y_out, par);
   c.y0 = sel(a.y0, par);
@@ -254,6 +256,7 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
 #pragma unroll
       for (int i = 0; i < VW; ++i) acc[i] = fadd(acc[i], fmul(cf, k[i]));
     }
+    float group = 0.f;  // the VW squared ratios are summed in fp32 first: one fp64 add per group
 #pragma unroll
     for (int i = 0; i < VW; ++i) {
       float tol = fadd(c.atol, fmul(c.rtol, fmaxf(fabsf(in.y0[i]), fabsf(in.y1[i]))));
@@ -265,8 +268,19 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
       float r2 = fmul(r, r);
       // torch.max propagates NaN, fmaxf does not: keep the poison visible to the controller
       if (!(r2 == r2) || in.y0[i] != in.y0[i] || in.y1[i] != in.y1[i]) r2 = __int_as_float(0x7fc00000);
-      err_acc += (double)r2;
+      group += r2;
     }
+    err_acc += (double)group;
+    return;
+  }
+
+  if (c.mode == EPI_MASK) {
+    // vjp of relu(pre): the cotangent passes where the forward value is positive (k = relu(pre) > 0 <=> pre > 0)
+    float out[VW];
+#pragma unroll
+    for (int i = 0; i < VW; ++i) out[i] = k[i] > 0.f ? fmul(c.coef[0], in.y0[i]) : 0.f;
+    if (stream_out) stv_stream<VW>(c.y_out + off, out);
+    else stv<VW>(c.y_out + off, out);
     return;
   }
 

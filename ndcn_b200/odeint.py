@@ -159,6 +159,15 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
                 out.copy_(res)
             else:
                 out = res.to(y0.device)
+    if (out is None and y0.is_cuda and y0.dim() == 2 and y0.dtype == torch.float32 and method in ("euler", "midpoint", "rk4")
+            and type(func).__name__ == "ODEFunc" and hasattr(func, "wt") and getattr(func.wt, "bias", None) is not None
+            and not (getattr(func, "dropout", 0.0) and getattr(func, "training", False))):
+        # training through a fixed-grid solver: fused forward + discrete adjoint on the library's kernels
+        bound = recognise(func, int(y0.shape[1]), y0.device)
+        if bound is not None and bound[0].n_rows == y0.shape[0]:
+            out = autograd_solver.solve_fixed_grid_fused(func, y0, t, method, bound[0], bound[1].flags)
+            if terminal_only:
+                out = out[-1]
     if out is None:
         require_cuda(y0.device if y0.is_cuda else None)
         if fused_kw:
