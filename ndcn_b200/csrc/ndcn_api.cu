@@ -357,7 +357,7 @@ static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_ou
   const int grid = (int)std::min<int64_t>(n_tiles, sm_count);
   *grid_out = grid;
   if (grid == 0) return 0;
-  const bool deep = ((u.dbg >> 8) & 1u) != 0;  // experiment switch: the other epilogue batch depth
+  const bool deep = u.deep_batch != 0;  // experiment switch: the other epilogue batch depth
 #define NDCN_UMMA_CASE(MODE, NPREV, B0, B1) \
   return deep ? launch_umma_inst<H, MODE, NPREV, B1>(u, e, grid, st) : launch_umma_inst<H, MODE, NPREV, B0>(u, e, grid, st)
   switch (e.mode) {
@@ -479,7 +479,7 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
           const char* v = std::getenv("NDCN_UMMA_DBG");
           return v ? (uint32_t)std::atoi(v) : 0u;
         }();
-        u.dbg = dbg;
+        u.deep_batch = (dbg >> 8) & 1u;
       }
       tick(NDCN_K_STAGE);
       rc = r.H == 256 ? launch_umma<256>(u, e, b.sm_count, &grid, st) : launch_umma<128>(u, e, b.sm_count, &grid, st);
@@ -1111,12 +1111,10 @@ struct Dopri {
   }
 
   int attempt() {
-    float* Yp = sv->Y[par];
     float* Yq = sv->Y[par ^ 1];
     float* KFq = sv->KF[par ^ 1];
     const PtrPair Ycur = pp(sv->Y[0], sv->Y[1]), Yoth = pp(sv->Y[1], sv->Y[0]);
     const PtrPair KFcur = pp(sv->KF[0], sv->KF[1]), KFoth = pp(sv->KF[1], sv->KF[0]);
-    (void)Yp;
     EpiArgs e = d.blank();
     e.ctrl = sv->ctrl;
     e.dt_src = DT_CTRL;

@@ -113,17 +113,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
-// TMA-engine flavour: 128 bytes starting at p (16-byte aligned) into L2, no LSU slot involved
-__device__ __forceinline__ void prefetch_l2_bulk128(const void* p) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(p) : "memory");
-}
-
-// L2 prefetch of the 128-byte line that holds elements [off, off + 32) of every stream the
-// epilogue will read (one line per lane and stream): the later loads then see L2 latency, not
-// HBM latency, so a handful of registers per lane is enough to keep the memory system busy.
 __device__ __forceinline__ void prefetch_l2_last(const void* p) {
   asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
 }
+// L2 prefetch (evict_last) of the 128-byte line that holds elements [off, off + 32) of every stream the
+// epilogue will read, one line per lane and stream: the demand loads a chunk later then see L2 latency,
+// not HBM latency.  Measured alternatives (profiles/README.md): evict_normal lines 1.6 % slower, two
+// chunks of lead 13 % slower (L2 thrash: 8 streams x 2 chunks x 148 SMs ~ 78 MB), the TMA flavour
+// (cp.async.bulk.prefetch.L2) 30-50 % slower, whole-tile prefetch 50 % slower.
 __device__ __forceinline__ void epi_prefetch_l2_last(const EpiCtx& c, int64_t off) {
   if (c.mode == EPI_STORE) return;
   prefetch_l2_last(c.y0 + off);
@@ -132,23 +129,6 @@ __device__ __forceinline__ void epi_prefetch_l2_last(const EpiCtx& c, int64_t of
   for (int j = 0; j < 6; ++j)
     if (j < c.n_prev) prefetch_l2_last(c.kprev[j] + off);
 }
-__device__ __forceinline__ void epi_prefetch_l2(const EpiCtx& c, int64_t off, bool bulk) {
-  if (c.mode == EPI_STORE) return;
-  if (bulk) {
-    prefetch_l2_bulk128(c.y0 + off);
-    if (c.mode == EPI_ERR) prefetch_l2_bulk128(c.y1 + off);
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      if (j < c.n_prev) prefetch_l2_bulk128(c.kprev[j] + off);
-  } else {
-    prefetch_l2(c.y0 + off);
-    if (c.mode == EPI_ERR) prefetch_l2(c.y1 + off);
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      if (j < c.n_prev) prefetch_l2(c.kprev[j] + off);
-  }
-}
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -192,8 +172,7 @@ struct UmmaArgs {
   // [H / bc][n_rows][bc] with bc = 1 << z_block_log2 >= 32 (the feature-sharded multi-GPU gather
   // delivers one [n_rows, H/P] block per peer and nobody has to interleave them)
   int z_block_log2;
-  uint32_t dbg;       // experiment switches (NDCN_UMMA_DBG): 1 no epilogue prefetch, 2 bulk (TMA) prefetch,
-                      // 4 prefetch lead 1 chunk instead of 2, 8 no producer prefetch
+  uint32_t deep_batch; // experiment switch (NDCN_UMMA_DBG=256): the other epilogue batch depth
 };
 
 // MODE / NPREV: the epilogue mode and the number of earlier stages it reads are compile-time
@@ -257,43 +236,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     const int half = warp >> 2;    // which half of the H columns
     float4* st4 = reinterpret_cast<float4*>(staging + warp * 32 * kUmmaStagePitch);
     const bool relu = !(a.flags & NDCN_F_NO_RELU);
-    const bool stream_out = (a.dbg & 16u) == 0 && (int64_t)a.n_rows * H * 4 > ((int64_t)256 << 20);
+    const bool stream_out = (int64_t)a.n_rows * H * 4 > ((int64_t)256 << 20);
     const int rsub = lane >> 3;    // after the transpose: 8 lanes x 16 bytes per row, 4 rows per instruction
     const int cg = lane & 7;
     constexpr int kChunks = H / 2 / 32;
-    // L2 prefetch lead in chunks: 1 measured best (2 thrashes L2 at the wide stages: 8 streams x
-    // 2 chunks x 148 SMs ~ 78 MB in flight; dbg bit 4 selects 2 for experiments)
-    const int kAhead = (a.dbg & 4u) ? 2 : 1;
-    const bool pf_on = !(a.dbg & 1u), pf_bulk = (a.dbg & 2u) != 0;
+    constexpr int kAhead = 1;      // chunks of L2 prefetch lead
     Tracer tr(warp == 0 && lane == 0 ? 3 : -1000000);
     // lane r prefetches row r of this warp's quadrant for chunk number g of the warp's own sequence
     auto prefetch_chunk = [&](int64_t g) {
       const int64_t ti = g / kChunks;
-      if (ti >= my_tiles || !pf_on) return;
-      const int64_t row = ((int64_t)blockIdx.x + ti * gridDim.x) * kUmmaM + q * 32 + lane;
-      if (row < a.n_rows) {
-        // evict_last: the prefetched lines survive the L2 churn until the demand load a chunk later
-        // (measured 1.61 -> 1.53 ms per stage kernel; dbg bit 64 falls back to evict_normal)
-        if (!(a.dbg & 64u)) epi_prefetch_l2_last(c, row * H + half * (H / 2) + (int)(g % kChunks) * 32);
-        else epi_prefetch_l2(c, row * H + half * (H / 2) + (int)(g % kChunks) * 32, pf_bulk);
-      }
-    };
-    // experiment (dbg bit 32): tile-granular prefetch -- lane r prefetches the whole half row (all
-    // chunks, contiguous 128-byte lines) of tile ti at once, one tile ahead
-    const bool pf_tile = (a.dbg & 32u) != 0;
-    auto prefetch_tile = [&](int64_t ti) {
       if (ti >= my_tiles) return;
       const int64_t row = ((int64_t)blockIdx.x + ti * gridDim.x) * kUmmaM + q * 32 + lane;
-      if (row < a.n_rows) {
-#pragma unroll
-        for (int cc = 0; cc < kChunks; ++cc) epi_prefetch_l2(c, row * H + half * (H / 2) + cc * 32, false);
-      }
+      if (row < a.n_rows) epi_prefetch_l2_last(c, row * H + half * (H / 2) + (int)(g % kChunks) * 32);
     };
-    if (pf_tile) {
-      prefetch_tile(0);
-    } else {
-      for (int g = 0; g < kAhead; ++g) prefetch_chunk(g);
-    }
+    for (int g = 0; g < kAhead; ++g) prefetch_chunk(g);
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
       const int acc = (int)(i & 1);
@@ -304,8 +260,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
 #pragma unroll 1
       for (int cc = 0; cc < kChunks; ++cc) {
         const int c0 = half * (H / 2) + cc * 32;
-        if (!pf_tile) prefetch_chunk(i * kChunks + cc + kAhead);
-        else if (cc == 0) prefetch_tile(i + 1);
+        prefetch_chunk(i * kChunks + cc + kAhead);
         // the stage-algebra loads run one batch ahead of the arithmetic (two register sets): the first
         // batch of a chunk is already in flight while the accumulators are read and transposed
         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * cg);
@@ -441,13 +396,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     };
     // lane r of producer warp pw prefetches (L2) the 128-byte atom row r of its 32 rows
     auto prefetch_atom = [&](int64_t it) {
-      if (it >= total || (a.dbg & 8u)) return;
+      if (it >= total) return;
       const int64_t tile = (int64_t)blockIdx.x + (it / Cf::kAtoms) * gridDim.x;
       const int64_t row = tile * kUmmaM + pw * 32 + lane;
-      if (row < a.n_rows) {
-        if (a.dbg & 128u) prefetch_l2_last(z_atom(row, (int)(it % Cf::kAtoms)));
-        else prefetch_l2(z_atom(row, (int)(it % Cf::kAtoms)));
-      }
+      if (row < a.n_rows) prefetch_l2(z_atom(row, (int)(it % Cf::kAtoms)));
     };
     constexpr int kAheadA = 4;
     Tracer tr(pw == 0 && lane == 0 ? 1 : -1000000);
