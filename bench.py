@@ -41,6 +41,10 @@ T_TOTAL, STEPS_TOTAL = 5.0, 100  # north star: T=5, 100 dopri5 steps  ->  dt = 0
 DT = T_TOTAL / STEPS_TOTAL
 
 
+PUSH_MAX_WORLD = 4  # above this the feature-sharded gather moves far fewer bytes than the push
+PUSH_IN_AUTO = False  # `--exchange auto` may pick the peer-push scheme (switched on once measured on the box)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -55,7 +59,7 @@ def parse_args():
     ap.add_argument("--adaptive", action="store_true",
                     help="dopri5 with the NDCN tolerances (rtol .01, atol .001) over T=5 instead of forced steps; "
                          "reports the measured accepted/rejected steps (SURVEY.md section 8(d)); single GPU")
-    ap.add_argument("--exchange", choices=["auto", "halo", "feature"], default="auto",
+    ap.add_argument("--exchange", choices=["auto", "halo", "feature", "push"], default="auto",
                     help="multi-GPU exchange scheme: halo rows of the row partition, feature-sharded gather, "
                          "or whichever moves fewer bytes per RHS (auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,6 +256,28 @@ def workload_config(args, n, nnz):
 
 # ----------------------------------------------------------------------------------------------
 # our arm
+def pick_exchange(vols: dict, world: int, H: int, allow_push: bool = True) -> str:
+    """`--exchange auto`.  Bytes per RHS and rank: halo and push move about the same on a graph without
+    locality, but push overlaps the transfer with the stage kernel and needs no pack pass, so it wins
+    wherever the halo exchange would be chosen on such a graph; the feature-sharded gather moves
+    2 (P-1)/P^2 of the state and takes over once that is far below the push volume (measured cross-over
+    on the 1M-node power-law graph: see profiles/README.md).  A graph WITH locality (halo much smaller
+    than the remote rows) keeps the NCCL halo exchange."""
+    feature_ok = vols.get("feature") is not None and H in (128, 256)
+    halo, push = vols["halo"], vols["push"]
+    if halo < 0.5 * push:
+        if feature_ok and vols["feature"] < halo:
+            return "feature"
+        return "halo"
+    if feature_ok and world >= PUSH_MAX_WORLD + 1 and vols["feature"] < push:
+        return "feature"
+    if allow_push and PUSH_IN_AUTO and world <= 8:
+        return "push"
+    if feature_ok and vols["feature"] < halo:
+        return "feature"
+    return "halo"
+
+
 # ----------------------------------------------------------------------------------------------
 def main_ours(args):
     import ndcn_b200 as nb
@@ -281,6 +307,7 @@ def main_ours(args):
 
     z_block_cols = 0
     vols = None
+    peers = None
     if world == 1:
         graph = nb.CsrGraph.from_scipy(phi, dev)
         exchange = None
@@ -288,17 +315,41 @@ def main_ours(args):
         part = None
     else:
         from ndcn_b200 import partition
-        # two exchange schemes (ndcn_b200/partition.py): halo rows of a 1-D row partition, or the
-        # feature-sharded gather; take the one that moves fewer bytes per RHS on this graph
+        # three exchange schemes (ndcn_b200/partition.py): NCCL halo exchange of a 1-D row partition, the
+        # feature-sharded gather (2 NCCL all-to-alls), or peer push (stage kernels store into IPC-mapped
+        # peer buffers); `auto` = pick_exchange()
         vols = partition.exchange_volumes(phi, world, H)
-        if args.exchange == "feature" or (args.exchange == "auto" and vols["feature"] is not None
-                                         and vols["feature"] < vols["halo"] and H in (128, 256)):
+        scheme = args.exchange
+        if scheme == "auto":
+            scheme = pick_exchange(vols, world, H)
+        peers = None
+        if scheme == "push":
+            # peer push needs CUDA IPC between the ranks' processes; agree collectively whether it came up
+            ok = torch.ones(1, device=dev)
+            try:
+                part = partition.PushPartition.build(phi, world, rank, dev, H, args.method if not args.adaptive else "dopri5")
+            except Exception as exc:  # pragma: no cover - depends on the box
+                print("rank %d: peer push unavailable (%s); falling back" % (rank, exc), file=sys.stderr)
+                ok.zero_()
+                part = None
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1.0:
+                if part is not None:
+                    part.close(group=False)
+                if args.exchange == "push":
+                    raise RuntimeError("--exchange push: CUDA IPC peer mapping failed on some rank")
+                scheme = pick_exchange(vols, world, H, allow_push=False)
+            else:
+                peers = part
+        if scheme == "push":
+            pass
+        elif scheme == "feature":
             part = partition.FeaturePartition(phi, world, rank, dev, H)
             z_block_cols = part.Hc
         else:
             part = partition.RowPartition.build(phi, world, rank, dev, H)
         graph = part.graph
-        exchange = part.exchange
+        exchange = part.exchange if peers is None else None
         x0 = x0_host[part.row0:part.row1].to(dev)
 
     K, Wm = args.steps, args.warmup
@@ -309,14 +360,14 @@ def main_ours(args):
         if args.adaptive:
             t = torch.tensor([0.0, T_TOTAL], dtype=torch.float64)
             return nb.odeint_fused(graph, spec, y0, t, method="dopri5", rtol=.01, atol=.001, terminal_only=True,
-                                   exchange=exchange, time_kernels=time_kernels, out=out, z_block_cols=z_block_cols)
+                                   exchange=exchange, time_kernels=time_kernels, out=out, z_block_cols=z_block_cols, peers=peers)
         if method == "dopri5":
             t = torch.tensor([0.0, DT * (k - 0.5)], dtype=torch.float64)  # inside the k-th step: exactly k steps
             return nb.odeint_fused(graph, spec, y0, t, method="dopri5", forced_dt=DT, terminal_only=True,
-                                   exchange=exchange, time_kernels=time_kernels, out=out, z_block_cols=z_block_cols)
+                                   exchange=exchange, time_kernels=time_kernels, out=out, z_block_cols=z_block_cols, peers=peers)
         t = torch.linspace(0, DT * k, k + 1, dtype=torch.float64)
         return nb.odeint_fused(graph, spec, y0, t, method=method, terminal_only=True, exchange=exchange,
-                               time_kernels=time_kernels, out=out, z_block_cols=z_block_cols)
+                               time_kernels=time_kernels, out=out, z_block_cols=z_block_cols, peers=peers)
 
     def barrier():
         if dist is not None:
@@ -380,10 +431,17 @@ def main_ours(args):
     except Exception:
         pass
     split = gather_n > 0
+    # which gather the library's auto rule picks (csrc/ndcn_api.cu::pick_gather_cw)
+    cw_cfg = int(_ffi.lib().ndcn_config_get(_ffi.CFG_GATHER_CW))
+    Hg = z_block_cols or H
+    slab_fits = Hg > 32 and graph.n_cols * Hg * 4 > (64 << 20) and graph.n_cols * 128 <= (48 << 20)
+    chunked = cw_cfg > 0 or (cw_cfg == 0 and (slab_fits or (Hg <= 64 and graph.n_cols >= 4096)))
+    gather_name = ("chunk-major CSR gather (k_stage_gather_chunk)" if chunked
+                   else "full-row CSR gather, one warp per row (k_stage_ndcn_row)")
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic,
-        "kernel": ("RHS evaluation = chunk-major CSR gather (k_stage_gather_chunk) + tcgen05 3xTF32 GEMM with bias/ReLU "
+        "kernel": (f"RHS evaluation = {gather_name} + tcgen05 3xTF32 GEMM with bias/ReLU "
                    "and RK stage epilogue (k_stage_gemm_umma); time = sum of the two launches") if split else
                   "fused RHS stage kernel (CSR gather + W GEMM + bias/ReLU + RK stage epilogue)",
         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": rhs_avg_ms, "launches_timed": int(stage_n),
@@ -454,7 +512,11 @@ def main_ours(args):
         "solver": {"nfe": info.nfe, "accepted": info.n_accepted, "rejected": info.n_rejected, "finite": finite},
     }
     if world > 1:
-        if z_block_cols:
+        if peers is not None:
+            line["config"]["parallelism"] = ("1-D node-row partition x%d, peer push: stage kernels store new rows into "
+                                             "the IPC-mapped gather sources of all peers (NVLink), device barrier "
+                                             "kernel per RHS eval, no NCCL on the path" % world)
+        elif z_block_cols:
             line["config"]["parallelism"] = ("1-D node-row partition x%d for the state / GEMM / solver algebra, "
                                              "feature-sharded gather: 2 NCCL all-to-alls per RHS eval" % world)
         else:

@@ -39,6 +39,7 @@ typedef struct ndcn_solver ndcn_solver_t;
 #define NDCN_E_NONFINITE (-10) /* "non-finite values in state `y`"  (dopri5.py:102)   */
 #define NDCN_E_DT_UNDERFLOW (-11) /* "underflow in dt"              (dopri5.py:100)   */
 #define NDCN_E_MAX_STEPS (-12) /* "max_num_steps exceeded"          (dopri5.py:89)    */
+#define NDCN_E_PEER_TIMEOUT (-13) /* peer push: another rank never reached a barrier (20 s)  */
 
 /* ---- right-hand sides -------------------------------------------------------------- */
 enum ndcn_rhs_kind {
@@ -134,7 +135,8 @@ enum ndcn_kernel_class {
   NDCN_K_CONTROL = 2, /* step-size controller / scalar reductions */
   NDCN_K_EMIT = 3,    /* dense output */
   NDCN_K_INIT = 4,    /* initial-step norms */
-  NDCN_K_GATHER = 5,  /* chunk-major gather z = Phi x feeding the tcgen05 GEMM stage kernel */
+  NDCN_K_GATHER = 5,  /* gather z = Phi x feeding the tcgen05 GEMM stage kernel */
+  NDCN_K_EXCHANGE = 6, /* peer-push barrier / all-reduce kernel (includes the wait for the slowest rank) */
   NDCN_K_CLASSES = 8
 };
 
@@ -194,6 +196,37 @@ int ndcn_solver_destroy(ndcn_solver_t* sv);
 int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t,
                     float* out, const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats,
                     ndcn_stream_t s);
+
+/* ---- multi-GPU peer push (new; the reference is single-device) ---------------------------
+ * The third exchange scheme of a 1-D row partition, and the one without a collective call on the
+ * path: the graph handle is built with a FULL halo (n_cols = all nodes; gather sources are laid out
+ * [own rows | rows of rank 0, 1, ... without the own block]), every rank maps the other ranks'
+ * workspaces (CUDA IPC, NVLink), and the kernels that produce a gather source (tcgen05 stage
+ * kernels, pre-stage algebra) store each new row into the local buffer AND into the halo region of
+ * every peer.  A one-block barrier kernel over IPC-shared signal pads orders those stores before
+ * the next gather and doubles as the 2-double all-reduce of the dopri5 controller, so the solve needs
+ * no exchange hook, no NCCL call and no host synchronisation per step.
+ *   pad[r]          device address (in THIS process) of rank r's 4 KB signal pad; pad[rank] = own,
+ *                   zero-initialised before the first solve (ndcn_peer_alloc does it)
+ *   delta_bytes[r]  distance in bytes from an element of one of this rank's gather-source buffers
+ *                   (row i of the own block) to the same element inside rank r's mapped workspace:
+ *                   (workspace_r - workspace_own) + halo_row_offset_of_my_block_at_r * H * 4.
+ *                   Gather sources sit at the same offset in every rank's workspace (they are sized
+ *                   by n_cols = all nodes), so one delta per peer covers Y[2] and YS[2].
+ * All ranks must run the same solves in the same order (identical control flow: the controller
+ * sees all-reduced sums).  A rank that waits 20 s at a barrier fails with NDCN_E_PEER_TIMEOUT.     */
+typedef struct ndcn_peer_config {
+  int32_t rank, world;      /* world <= 8 */
+  void* pad[8];
+  int64_t delta_bytes[8];   /* entry `rank` ignored */
+} ndcn_peer_config_t;
+int ndcn_solver_set_peers(ndcn_solver_t* sv, const ndcn_peer_config_t* cfg /* NULL: off */);
+/* cudaMalloc + cudaIpcGetMemHandle (64-byte handle); the first 4 KB are zeroed (signal pad) */
+int ndcn_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
+int ndcn_peer_open(const unsigned char* handle, void** ptr_out); /* cudaIpcOpenMemHandle */
+int ndcn_peer_close(void* ptr);
+int ndcn_peer_free(void* ptr);
+int ndcn_peer_enable_access(int peer_device); /* same-process peers (tests): cudaDeviceEnablePeerAccess */
 
 /* ---- solver algebra as stand-alone kernels (used by tests and by generic callers) ----- */
 /* out = y0 + sum_j (dt*beta_j) k_j, reference rounding (misc.py:22-25, rk_common.py:50) */

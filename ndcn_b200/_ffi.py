@@ -21,7 +21,7 @@ EXCHANGE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 # status codes (include/ndcn_b200.h)
 OK = 0
 E_ARG, E_WORKSPACE, E_METHOD = -1, -2, -3
-E_NONFINITE, E_DT_UNDERFLOW, E_MAX_STEPS = -10, -11, -12
+E_NONFINITE, E_DT_UNDERFLOW, E_MAX_STEPS, E_PEER_TIMEOUT = -10, -11, -12, -13
 
 RHS_NDCN, RHS_HEAT, RHS_GENE, RHS_MUTUAL, RHS_CALLBACK_KIND = 0, 1, 2, 3, 4
 F_NO_GRAPH, F_NO_CONTROL, F_NO_RELU = 1, 2, 4
@@ -29,7 +29,7 @@ EULER, MIDPOINT, RK4, DOPRI5 = 0, 1, 2, 3
 METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4, "dopri5": DOPRI5}
 O_TERMINAL_ONLY, O_FORCED_DT, O_TIME_KERNELS = 1, 2, 4
 GATHER_LOCAL, GATHER_EXTERNAL = 0, 1
-K_STAGE, K_ALGEBRA, K_CONTROL, K_EMIT, K_INIT, K_GATHER = 0, 1, 2, 3, 4, 5
+K_STAGE, K_ALGEBRA, K_CONTROL, K_EMIT, K_INIT, K_GATHER, K_EXCHANGE = 0, 1, 2, 3, 4, 5, 6
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
 CFG_STAGE_IMPL, CFG_GATHER_CW, CFG_UMMA_MIN_ROWS, CFG_GATHER_VERSION = 0, 1, 2, 3
 
@@ -52,6 +52,12 @@ class SolveOpts(C.Structure):
         ("gather_mode", C.c_int32), ("z_block_cols", C.c_int32),
         ("dec_W", C.c_void_p), ("dec_b", C.c_void_p), ("dec_classes", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class PeerConfig(C.Structure):
+    """``ndcn_peer_config_t``: the peer-push multi-GPU scheme (partition.PushPartition)."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("pad", C.c_void_p * 8), ("delta_bytes", C.c_int64 * 8)]
 
 
 class GatherRequest(C.Structure):
@@ -88,6 +94,12 @@ PROTOTYPES = {
                                        C.c_void_p, C.c_void_p]),
     "ndcn_pack_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_pack_cols_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ndcn_solver_set_peers": (C.c_int, [C.c_void_p, C.POINTER(PeerConfig)]),
+    "ndcn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ndcn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ndcn_peer_close": (C.c_int, [C.c_void_p]),
+    "ndcn_peer_free": (C.c_int, [C.c_void_p]),
+    "ndcn_peer_enable_access": (C.c_int, [C.c_int]),
     "ndcn_config_set": (C.c_int, [C.c_int32, C.c_int64]),
     "ndcn_config_get": (C.c_int64, [C.c_int32]),
     "ndcn_debug_umma_trace": (C.c_int, [C.c_void_p]),
@@ -136,6 +148,7 @@ _MESSAGES = {
     E_NONFINITE: "non-finite values in state `y`",
     E_DT_UNDERFLOW: "underflow in dt",
     E_MAX_STEPS: "max_num_steps exceeded",
+    E_PEER_TIMEOUT: "peer push: another rank did not reach the barrier within 20 s",
 }
 
 

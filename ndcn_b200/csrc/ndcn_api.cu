@@ -161,6 +161,10 @@ struct ndcn_solver {
   Ctrl* ctrl_host = nullptr;  // pinned
   int64_t launches = 0;
   int sm_count = 148;
+  // multi-GPU peer push (ndcn_solver_set_peers): world > 1 switches it on
+  PeerArgs peers{};
+  int n_push = 0;                      // world - 1
+  long long push_delta[kMaxPeers] = {};  // byte distance local gather-source element -> the same element at peer j
 };
 
 // ---------------------------------------------------------------------------------------
@@ -852,6 +856,8 @@ extern "C" int ndcn_solver_create(const ndcn_graph_t* g, const ndcn_rhs_desc_t* 
   int rc = (int)cudaMalloc((void**)&sv->partials, sizeof(double) * 2 * sv->max_partials);
   if (!rc) rc = (int)cudaMalloc((void**)&sv->xchg, sizeof(double) * 4);
   if (!rc) rc = (int)cudaMalloc((void**)&sv->t_stage, sizeof(float) * 4);
+  sv->t_cap = 128;  // requested output times; grown on demand (never inside a peer-push solve's barriers)
+  if (!rc) rc = (int)cudaMalloc((void**)&sv->t_out, sizeof(double) * sv->t_cap);
   if (!rc) rc = (int)cudaMalloc((void**)&sv->ctrl, sizeof(Ctrl));
   if (!rc) rc = (int)cudaMallocHost((void**)&sv->ctrl_host, sizeof(Ctrl));
   if (rc) {
@@ -927,13 +933,43 @@ struct Driver : StageTimer {
     evs.clear();
   }
 
+  bool push() const { return sv->n_push > 0; }
+  bool multi() const { return o->exchange != nullptr || push(); }
+
+  // every y_out of a solve is a gather source: on a peer-push solve it is also stored at the peers
   EpiArgs blank() const {
     EpiArgs e;
     std::memset(&e, 0, sizeof(e));
+    e.n_peers = sv->n_push;
+    for (int j = 0; j < sv->n_push; ++j) e.peer_delta[j] = sv->push_delta[j];
     return e;
   }
 
-  int exchange(float* buf) {  // fill halo rows of a gather source (multi-GPU hook)
+  // peer push: all ranks' stores into each other's gather sources are complete and visible after this;
+  // with a payload also the all-reduce (SUM) of two doubles in place
+  int peer_barrier(double* payload) {
+    sv->launches += 1;
+    t_begin(NDCN_K_EXCHANGE);
+    k_peer_barrier<<<1, 32, 0, st>>>(sv->peers, payload, sv->ctrl);
+    t_end();
+    return (int)cudaGetLastError();
+  }
+
+  // all-reduce (SUM) of the 2 doubles at sv->xchg across ranks: device barrier kernel or the host hook
+  int allreduce_xchg() {
+    if (push()) return peer_barrier(sv->xchg);
+    return o->exchange(o->exchange_user, 1, sv->xchg);
+  }
+
+  // gather source `buf` -> also into the halo region of every peer (peer push: initial state)
+  int push_copy(float* buf) {
+    for (int j = 0; j < sv->n_push; ++j)
+      CU_TRY(cudaMemcpyAsync((char*)buf + sv->push_delta[j], buf, sizeof(float) * (size_t)sv->numel, cudaMemcpyDefault, st));
+    return 0;
+  }
+
+  int exchange(float* buf) {  // make the halo rows of a gather source valid (multi-GPU)
+    if (push()) return peer_barrier(nullptr);
     if (o->exchange && sv->n_cols > sv->n_rows) return o->exchange(o->exchange_user, 0, buf);
     return 0;
   }
@@ -1020,7 +1056,9 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
     CU_TRY(cudaMemcpyAsync(out, y0, bytes, cudaMemcpyDeviceToDevice, st));
     cur = out;
   } else {
+    if (d.push()) RC_TRY(d.peer_barrier(nullptr));
     CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
+    RC_TRY(d.push_copy(sv->Y[0]));
     if (!terminal) RC_TRY(d.put_state(out, 0, y0));
     cur = sv->Y[0];
   }
@@ -1095,7 +1133,7 @@ struct Dopri {
   }
 
   int reduce_and_control(int n_partials) {
-    const bool multi = d.o->exchange != nullptr;
+    const bool multi = d.multi();
     if (!multi) {
       sv->launches += 1;
       d.t_begin(NDCN_K_CONTROL);
@@ -1104,7 +1142,7 @@ struct Dopri {
     } else {
       sv->launches += 2;
       k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 1);
-      RC_TRY(d.o->exchange(d.o->exchange_user, 1, sv->xchg));
+      RC_TRY(d.allreduce_xchg());
       k_controller<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, sv->t_out, sv->xchg, 2);
     }
     return (int)cudaGetLastError();
@@ -1164,14 +1202,14 @@ struct Dopri {
   }
 
   int init_scalar(int n_partials, int phase, double t_first) {
-    const bool multi = d.o->exchange != nullptr;
+    const bool multi = d.multi();
     if (!multi) {
       sv->launches += 1;
       k_init_scalar<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, phase, t_first, sv->xchg, 0);
     } else {
       sv->launches += 2;
       k_init_scalar<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, phase, t_first, sv->xchg, 1);
-      RC_TRY(d.o->exchange(d.o->exchange_user, 1, sv->xchg));
+      RC_TRY(d.allreduce_xchg());
       k_init_scalar<<<1, kStageThreadsCtl, 0, d.st>>>(sv->ctrl, sv->partials, n_partials, phase, t_first, sv->xchg, 2);
     }
     return (int)cudaGetLastError();
@@ -1212,7 +1250,9 @@ struct Dopri {
     h.n_out = n_t;
     h.emit_lo = h.emit_hi = 1;
     h.terminal_only = terminal ? 1 : 0;
-    if (d.o->exchange) {
+    if (d.push()) {
+      h.numel_global = (double)sv->n_cols * (double)sv->H;  // full halo: n_cols = all nodes
+    } else if (d.o->exchange) {
       // global element count = all-reduce of the local one (same hook, what = 1)
       double tmp[2] = {(double)sv->numel, 0.0};
       CU_TRY(cudaMemcpyAsync(sv->xchg, tmp, sizeof(tmp), cudaMemcpyHostToDevice, st));
@@ -1224,7 +1264,10 @@ struct Dopri {
     CU_TRY(cudaMemcpyAsync(sv->ctrl, &h, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));  // ctrl_host is reused as the poll target below
 
+    // peer push: nobody may still be reading the halo rows of an earlier solve when y0 arrives
+    if (d.push()) RC_TRY(d.peer_barrier(nullptr));
     CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
+    RC_TRY(d.push_copy(sv->Y[0]));
     if (!terminal) RC_TRY(d.put_state(out, 0, y0));
 
     emit.ctrl = sv->ctrl;
@@ -1313,6 +1356,7 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   sv->launches = 0;
   Driver d(sv, opts, st);
   d.vec_ok = aligned16(out) && aligned16(y0) && (sv->numel % 4 == 0);
+  for (int j = 0; j < sv->n_push; ++j) d.vec_ok = d.vec_ok && (sv->push_delta[j] % 16 == 0);  // peer copies of 16-byte stores
   d.timing = (opts->flags & NDCN_O_TIME_KERNELS) != 0;
   if (stats) std::memset(stats, 0, sizeof(*stats));
   std::memset(sv->ctrl_host, 0, sizeof(Ctrl));
@@ -1367,6 +1411,76 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   }
   if (rc != 0) return rc;
   return sv->ctrl_host->status;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU peer push: configuration and IPC-shareable allocations
+// ---------------------------------------------------------------------------------------
+extern "C" int ndcn_solver_set_peers(ndcn_solver_t* sv, const ndcn_peer_config_t* cfg) {
+  if (!sv) return NDCN_E_ARG;
+  sv->n_push = 0;
+  std::memset(&sv->peers, 0, sizeof(sv->peers));
+  if (!cfg || cfg->world <= 1) return NDCN_OK;
+  if (cfg->world > kMaxPeers + 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return NDCN_E_ARG;
+  if (sv->n_cols <= sv->n_rows) return NDCN_E_ARG;  // needs halo rows to push into
+  if (sv->rhs.kind == NDCN_RHS_CALLBACK) return NDCN_E_ARG;
+  for (int r = 0; r < cfg->world; ++r)
+    if (!cfg->pad[r] || ((uintptr_t)cfg->pad[r] & 15u)) return NDCN_E_ARG;
+  sv->peers.self = (PeerPad*)cfg->pad[cfg->rank];
+  sv->peers.rank = cfg->rank;
+  sv->peers.world = cfg->world;
+  int j = 0;
+  for (int r = 0; r < cfg->world; ++r) {
+    sv->peers.peer[r] = (PeerPad*)cfg->pad[r];
+    if (r == cfg->rank) continue;
+    if (cfg->delta_bytes[r] % 4 != 0) return NDCN_E_ARG;
+    sv->push_delta[j++] = (long long)cfg->delta_bytes[r];
+  }
+  sv->n_push = cfg->world - 1;
+  return NDCN_OK;
+}
+
+extern "C" int ndcn_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out /* 64 bytes */) {
+  if (!ptr_out || !handle_out || bytes == 0) return NDCN_E_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, bytes));
+  cudaError_t ce = cudaMemset(p, 0, std::min<size_t>(bytes, 4096));  // the PeerPad head starts at epoch 0
+  cudaIpcMemHandle_t h;
+  if (ce == cudaSuccess) ce = cudaIpcGetMemHandle(&h, p);
+  if (ce != cudaSuccess) {
+    cudaFree(p);
+    return (int)ce;
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return NDCN_OK;
+}
+
+extern "C" int ndcn_peer_open(const unsigned char* handle, void** ptr_out) {
+  if (!handle || !ptr_out) return NDCN_E_ARG;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return NDCN_OK;
+}
+
+extern "C" int ndcn_peer_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : NDCN_OK; }
+extern "C" int ndcn_peer_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : NDCN_OK; }
+
+// same-process, same-device stand-in for the IPC mapping (tests: two "ranks" as two threads on one GPU)
+extern "C" int ndcn_peer_enable_access(int peer_device) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev == peer_device) return NDCN_OK;
+  cudaError_t ce = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (ce == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return NDCN_OK;
+  }
+  return (int)ce;
 }
 
 // ---------------------------------------------------------------------------------------

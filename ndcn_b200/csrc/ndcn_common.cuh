@@ -15,6 +15,7 @@ namespace ndcn {
 constexpr int kStageThreadsCtl = 256;  // block size of the single-block scalar kernels
 constexpr int kStageThreads = 256;     // block size of every stage / elementwise kernel
 constexpr int kWarpsPerCta = kStageThreads / 32;
+constexpr int kMaxPeers = 7;           // other ranks of one NVSwitch domain (8 GPUs)
 
 // ------------------------------------------------------------------------------------
 // Device-resident controller block: the adaptive solver's scalars never visit the host
@@ -71,6 +72,10 @@ struct EpiArgs {
   float dt_host;
   float rtol, atol;
   double* partials;   // [gridDim.x] per-CTA partial sums (EPI_ERR)
+  // multi-GPU peer push (ndcn_solver_set_peers): every y_out element is also stored into the gather-source
+  // buffers of the other ranks, peer_delta[j] BYTES away from the local address (NVLink peer stores)
+  int n_peers;
+  long long peer_delta[kMaxPeers];
 };
 
 struct EpiCtx {  // EpiArgs resolved against the controller, per thread
@@ -84,6 +89,8 @@ struct EpiCtx {  // EpiArgs resolved against the controller, per thread
   float coef_fresh;  // coefficient of the k still in registers (= coef[n_prev])
   float dt;
   float rtol, atol;
+  int n_peers;
+  long long peer_delta[kMaxPeers];
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -126,6 +133,9 @@ __device__ __forceinline__ bool epi_resolve(const EpiArgs& a, EpiCtx& c) {
   c.dt = dt;
   c.rtol = a.rtol;
   c.atol = a.atol;
+  c.n_peers = a.n_peers;
+#pragma unroll
+  for (int j = 0; j < kMaxPeers; ++j) c.peer_delta[j] = a.peer_delta[j];
   return true;
 }
 
@@ -172,6 +182,20 @@ __device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[VW])
     *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
   } else {
     *p = v[0];
+  }
+}
+
+// y_out store: the local copy and, on a peer-push multi-GPU solve, the same elements in every other
+// rank's gather-source buffer (plain stores over NVLink; ordered by the k_peer_barrier that follows)
+template <int VW>
+__device__ __forceinline__ void store_y(const EpiCtx& c, int64_t off, const float (&v)[VW], bool stream_out) {
+  if (stream_out) stv_stream<VW>(c.y_out + off, v);
+  else stv<VW>(c.y_out + off, v);
+  if (c.n_peers > 0) {
+    char* base = reinterpret_cast<char*>(c.y_out + off);
+#pragma unroll
+    for (int j = 0; j < kMaxPeers; ++j)
+      if (j < c.n_peers) stv<VW>(reinterpret_cast<float*>(base + c.peer_delta[j]), v);
   }
 }
 
@@ -233,8 +257,7 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
     float out[VW];
 #pragma unroll
     for (int i = 0; i < VW; ++i) out[i] = fadd(in.y0[i], acc[i]);
-    if (stream_out) stv_stream<VW>(c.y_out + off, out);
-    else stv<VW>(c.y_out + off, out);
+    store_y<VW>(c, off, out, stream_out);
     return;
   }
 
@@ -304,8 +327,7 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
       out[i] = fadd(in.y0[i], fmul(s, dt8));
     }
   }
-  if (stream_out) stv_stream<VW>(c.y_out + off, out);
-    else stv<VW>(c.y_out + off, out);
+  store_y<VW>(c, off, out, stream_out);
 }
 
 template <int VW>

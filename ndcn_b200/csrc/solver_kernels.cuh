@@ -22,6 +22,97 @@ __device__ __forceinline__ double block_sum_partials(const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
+// Multi-GPU peer push (one process per GPU, buffers mapped into each other with CUDA IPC, NVLink):
+// the stage kernels store every new gather-source row straight into the other ranks' buffers
+// (store_y, ndcn_common.cuh); this one-block kernel is the barrier that separates those stores from
+// the gathers that read them, and -- with a payload -- the all-reduce (SUM, fixed rank order, so every
+// rank gets the same bits) of the two doubles the step controller needs.  Each rank owns one PeerPad
+// in IPC-shared memory: rank r announces epoch e by a system-scope release store into flag[r] of every
+// OTHER rank's pad and spins (acquire) on its own pad, i.e. on local memory.  A rank can be at most one
+// epoch ahead of the slowest one, so two payload slots (epoch parity) are enough.
+// ---------------------------------------------------------------------------------------
+struct PeerPad {
+  unsigned long long flag[8];   // flag[r]: last epoch rank r announced (written remotely by rank r)
+  double pay[2][8][2];          // pay[epoch & 1][r]: rank r's addends
+  unsigned long long epoch;     // barriers this rank has executed (owner only)
+  int timed_out;                // owner only: a peer never arrived
+  int pad_;
+};
+static_assert(sizeof(PeerPad) <= 4096, "PeerPad must fit the 4 KB head of the shared allocation");
+
+struct PeerArgs {
+  PeerPad* self;
+  PeerPad* peer[8];  // [world], entry `rank` unused
+  int rank, world;
+};
+
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(32) k_peer_barrier(PeerArgs a, double* payload, Ctrl* ctrl) {
+  __shared__ unsigned long long s_epoch;
+  const int j = threadIdx.x;
+  PeerPad* self = a.self;
+  if (j == 0) {
+    s_epoch = self->epoch + 1;
+    self->epoch = s_epoch;
+  }
+  __syncwarp();
+  const unsigned long long ep = s_epoch;
+  const bool active = j < a.world && j != a.rank;
+  const int slot = (int)(ep & 1ull);
+  if (active) {
+    PeerPad* p = a.peer[j];
+    if (payload != nullptr) {
+      volatile double* dst = &p->pay[slot][a.rank][0];
+      dst[0] = payload[0];
+      dst[1] = payload[1];
+    }
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&p->flag[a.rank]), "l"(ep) : "memory");
+    // wait for rank j on local memory
+    if (!*(volatile int*)&self->timed_out) {
+      const unsigned long long t0 = global_timer_ns();
+      unsigned long long seen = 0;
+      unsigned int spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&self->flag[j]) : "memory");
+        if (seen >= ep) break;
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > kPeerTimeoutNs) {
+          *(volatile int*)&self->timed_out = 1;
+          if (ctrl != nullptr) {
+            ((volatile Ctrl*)ctrl)->status = NDCN_E_PEER_TIMEOUT;
+            ((volatile Ctrl*)ctrl)->done = 1;
+          }
+          break;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (payload != nullptr && j == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int r = 0; r < a.world; ++r) {
+      if (r == a.rank) {
+        s0 += payload[0];
+        s1 += payload[1];
+      } else {
+        const volatile double* src = &self->pay[slot][r][0];
+        s0 += src[0];
+        s1 += src[1];
+      }
+    }
+    payload[0] = s0;
+    payload[1] = s1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Accept / reject + next step size.  One block; thread 0 does the float64 scalar work.
 // `reduce_stage`: 0 = sum partials and (single GPU) decide immediately;
 //                 1 = only sum partials into xchg[0..1] (multi-GPU: the host hook all-reduces);

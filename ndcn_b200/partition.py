@@ -20,7 +20,18 @@ whole graph and gathers ALL rows on its own H/P-column slice:
     rows x all columns --all_to_all--> all rows x my columns --Phi--> --all_to_all--> rows x all columns
 The second all-to-all delivers one [n_local, H/P] block per peer; the tcgen05 stage kernel reads
 that blocked layout directly (``ndcn_solve_opts_t::z_block_cols``), so nothing is interleaved.
-``choose_partition`` picks the scheme with the smaller exchange volume.
+``exchange_volumes`` reports the bytes either scheme moves (``bench.py --exchange auto`` picks by it).
+
+``PushPartition`` is the third scheme and the only one without a collective call on the path: the
+local CSR takes a FULL halo (every remote row, ``n_cols`` = all nodes), every rank maps the other ranks'
+solver workspaces with CUDA IPC (NVLink peer memory), and the kernels that produce a gather source
+(tcgen05 stage kernels, pre-stage algebra) store each new row into their own buffer and into the halo
+region of every peer while they compute -- the all-gather of the north star, fused into the producing
+kernel's epilogue.  A one-block barrier kernel over IPC-shared signal pads (``k_peer_barrier``) orders
+those stores before the next gather and carries the dopri5 controller's 2-double all-reduce, so a solve
+issues no NCCL call, no Python hook and no per-step host synchronisation.  Volume per RHS and rank:
+(P-1) * n_local * H * 4 bytes out -- 512 MB at P=2 (what the halo exchange moves too, but overlapped with
+the stage kernel and without the pack pass), 896 MB at P=8 (there the feature-sharded scheme moves 224 MB).
 """
 from __future__ import annotations
 
@@ -66,8 +77,19 @@ class LocalBlock:
         return int(len(self.halo_global))
 
 
-def build_local_block(phi, world: int, rank: int) -> LocalBlock:
-    """Slice rows [row0,row1) of the scipy CSR operator and remap its columns."""
+def halo_row_offset(bounds: np.ndarray, src_rank: int, dst_rank: int) -> int:
+    """Full-halo layout: the row of ``dst_rank``'s gather-source buffer at which ``src_rank``'s block
+    starts.  A buffer is [own rows | all remote rows in global order], so the blocks of lower ranks
+    follow the own block directly and the blocks of higher ranks sit at their global offset."""
+    assert src_rank != dst_rank
+    n_local_dst = int(bounds[dst_rank + 1] - bounds[dst_rank])
+    row0_src = int(bounds[src_rank])
+    return row0_src + (n_local_dst if src_rank < dst_rank else 0)
+
+
+def build_local_block(phi, world: int, rank: int, full_halo: bool = False) -> LocalBlock:
+    """Slice rows [row0,row1) of the scipy CSR operator and remap its columns.  ``full_halo``: the halo
+    is EVERY remote row, referenced or not (peer-push scheme: remote blocks arrive whole)."""
     phi = phi.tocsr()
     n = phi.shape[0]
     bounds = row_blocks(n, world)
@@ -76,7 +98,10 @@ def build_local_block(phi, world: int, rank: int) -> LocalBlock:
     blk.sort_indices()
     col = blk.indices.astype(np.int64)
     local = (col >= r0) & (col < r1)
-    halo_global = np.unique(col[~local])
+    if full_halo:
+        halo_global = np.concatenate([np.arange(0, r0, dtype=np.int64), np.arange(r1, n, dtype=np.int64)])
+    else:
+        halo_global = np.unique(col[~local])
     new_col = np.empty_like(col)
     new_col[local] = col[local] - r0
     new_col[~local] = (r1 - r0) + np.searchsorted(halo_global, col[~local])
@@ -265,10 +290,128 @@ class FeaturePartition:
                 "all_to_all_bytes_per_rhs": per_rank, "exchanges": self.n_exchanges}
 
 
+class PushPartition:
+    """Peer-push scheme (module docstring): full-halo local graph + IPC-mapped workspaces.
+
+    ``graph`` / ``workspace_ptr`` / ``workspace_bytes`` / ``peer_config()`` are what
+    ``solver.odeint_fused(..., peers=part)`` needs.  Build with ``PushPartition.build`` (one process per
+    GPU, handles exchanged through the process group) or ``build_in_process`` (all ranks in one process,
+    e.g. two threads on one GPU in the tests: the device addresses are valid as they are).
+    """
+
+    PAD_BYTES = 4096
+
+    def __init__(self, block: LocalBlock, device: torch.device, H: int, method: str = "dopri5"):
+        self.block = block
+        self.device = device
+        self.H = int(H)
+        self.method = method
+        self.rank, self.world = block.rank, block.world
+        if self.world > 8:
+            raise ValueError("peer push covers one NVSwitch domain (world <= 8), got %d" % self.world)
+        self.bounds = block.bounds
+        self.row0, self.row1 = int(block.bounds[self.rank]), int(block.bounds[self.rank + 1])
+        self.n_local, self.n_halo = block.n_local, block.n_halo
+        self.n = self.n_local + self.n_halo
+        self.graph = CsrGraph(torch.from_numpy(block.rowptr).to(device), torch.from_numpy(block.col).to(device),
+                              torch.from_numpy(block.val).to(device), self.n_local, self.n)
+        lib = _ffi.lib()
+        with torch.cuda.device(device):
+            self.workspace_bytes = int(lib.ndcn_solver_workspace_bytes(self.n_local, self.n, self.H, _ffi.METHODS[method]))
+            ptr = C.c_void_p()
+            self._handle = C.create_string_buffer(64)
+            _ffi.check(lib.ndcn_peer_alloc(self.PAD_BYTES + self.workspace_bytes, C.byref(ptr), self._handle),
+                       "ndcn_peer_alloc")
+        self.base_ptr = int(ptr.value)
+        self.mapped: List[int] = []   # base address of every rank's allocation in THIS process
+        self._opened: List[int] = []
+        self.n_solves = 0
+
+    # ---- construction ----------------------------------------------------------------------
+    @classmethod
+    def build(cls, phi, world: int, rank: int, device: torch.device, H: int, method: str = "dopri5",
+              group=None) -> "PushPartition":
+        """One process per GPU: exchange the 64-byte IPC handles through the process group and map the
+        peers (``cudaIpcOpenMemHandle``; the peers' GPUs must be reachable over NVLink / PCIe P2P)."""
+        import torch.distributed as dist
+
+        self = cls(build_local_block(phi, world, rank, full_halo=True), device, H, method)
+        handles: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(handles, bytes(self._handle.raw), group=group)
+        lib = _ffi.lib()
+        with torch.cuda.device(device):
+            for r in range(world):
+                if r == rank:
+                    self.mapped.append(self.base_ptr)
+                    continue
+                p = C.c_void_p()
+                _ffi.check(lib.ndcn_peer_open(handles[r], C.byref(p)), "ndcn_peer_open")
+                self.mapped.append(int(p.value))
+                self._opened.append(int(p.value))
+        dist.barrier(group=group)  # everybody has mapped everybody before the first push
+        return self
+
+    @classmethod
+    def build_in_process(cls, phi, world: int, devices, H: int, method: str = "dopri5") -> List["PushPartition"]:
+        """All ranks inside one process (tests): rank r lives on ``devices[r]`` (the same GPU is fine)."""
+        parts = [cls(build_local_block(phi, world, r, full_halo=True), torch.device(devices[r]), H, method)
+                 for r in range(world)]
+        lib = _ffi.lib()
+        for a in parts:
+            a.mapped = [b.base_ptr for b in parts]
+            with torch.cuda.device(a.device):
+                for b in parts:
+                    if b.device != a.device:
+                        _ffi.check(lib.ndcn_peer_enable_access(b.device.index), "ndcn_peer_enable_access")
+        return parts
+
+    # ---- what the solver needs ---------------------------------------------------------------
+    @property
+    def workspace_ptr(self) -> int:
+        return self.base_ptr + self.PAD_BYTES
+
+    def peer_config(self) -> "_ffi.PeerConfig":
+        assert len(self.mapped) == self.world, "peers not mapped yet"
+        cfg = _ffi.PeerConfig()
+        cfg.rank, cfg.world = self.rank, self.world
+        own_ws = self.base_ptr + self.PAD_BYTES
+        for r in range(self.world):
+            cfg.pad[r] = self.mapped[r]
+            if r != self.rank:
+                rows = halo_row_offset(self.bounds, self.rank, r)
+                cfg.delta_bytes[r] = (self.mapped[r] + self.PAD_BYTES - own_ws) + rows * self.H * 4
+        return cfg
+
+    def describe(self) -> dict:
+        return {"scheme": "peer push (stage-kernel stores into IPC-mapped peer buffers + device barrier)",
+                "rows_local": self.n_local, "halo_rows": self.n_halo,
+                "push_bytes_per_rhs": (self.world - 1) * self.n_local * self.H * 4, "solves": self.n_solves}
+
+    def close(self, group=None) -> None:
+        """Unmap the peers, then (after everybody has unmapped) free the own allocation."""
+        lib = _ffi.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                lib.ndcn_peer_close(p)
+            self._opened = []
+            if group is not False:
+                try:
+                    import torch.distributed as dist
+                    if dist.is_available() and dist.is_initialized():
+                        dist.barrier(group=group)
+                except Exception:
+                    pass
+            if self.base_ptr:
+                lib.ndcn_peer_free(self.base_ptr)
+                self.base_ptr = 0
+
+
 def exchange_volumes(phi, world: int, H: int) -> dict:
     """Bytes one rank receives per RHS evaluation under either scheme (rank 0's block as the sample)."""
     blk = build_local_block(phi, world, 0)
     return {"halo": int(blk.n_halo) * H * 4,
+            "push": (world - 1) * blk.n_local * H * 4,
             "feature": 2 * (world - 1) * blk.n_local * (H // world) * 4 if H % (32 * world) == 0 else None}
 
 

@@ -142,7 +142,8 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
                  exchange: Optional[Callable] = None, out: Optional[torch.Tensor] = None,
                  time_kernels: bool = False, first_step: Optional[float] = None, safety: float = 0.0,
                  ifactor: float = 0.0, dfactor: float = 0.0, z_block_cols: int = 0,
-                 decoder: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None) -> torch.Tensor:
+                 decoder: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None,
+                 peers=None) -> torch.Tensor:
     """``torchdiffeq.odeint`` for a recognised RHS, entirely inside the CUDA library.
 
     y0: [n_rows, H] fp32 CUDA.  t: 1-D float tensor (any device); the values are used as
@@ -152,7 +153,10 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
     ``decoder=(W_d, b_d)``: apply ``Linear(H -> C)`` (NDCN.output_layer) to every returned state inside
     the solve; the result is ``[len(t), n_rows, C]`` and the ``[len(t), n_rows, H]`` slab is never written.
     ``exchange`` / ``z_block_cols``: multi-GPU hooks of ``ndcn_b200.partition`` (halo exchange of a
-    1-D row partition, or the feature-sharded gather).
+    1-D row partition, or the feature-sharded gather).  ``peers``: a ``partition.PushPartition`` -- the
+    peer-push scheme (no hook: the solve runs in the partition's IPC-shared workspace and the library's
+    kernels store new gather-source rows straight into the other ranks' buffers); ``graph`` must be
+    ``peers.graph`` and every rank must make the same calls in the same order.
     """
     global last_solve_info
     if method not in _ffi.METHODS:
@@ -213,17 +217,28 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
         opts.gather_mode, opts.z_block_cols = _ffi.GATHER_EXTERNAL, int(z_block_cols)
     stats = _ffi.SolveStats()
     with torch.cuda.device(dev):
-        nbytes = lib.ndcn_solver_workspace_bytes(graph.n_rows, graph.n_cols, spec.H, method_id)
-        ws = _workspace(dev, int(nbytes))
+        nbytes = int(lib.ndcn_solver_workspace_bytes(graph.n_rows, graph.n_cols, spec.H, method_id))
+        if peers is not None:
+            if exchange is not None or z_block_cols or spec.callback is not None:
+                raise ValueError("peers= excludes exchange hooks and callback right-hand sides")
+            if graph is not peers.graph or peers.H != spec.H or peers.workspace_bytes < nbytes:
+                raise ValueError("peers was built for another graph / width / method")
+            ws_ptr, ws_bytes = peers.workspace_ptr, peers.workspace_bytes
+        else:
+            ws = _workspace(dev, nbytes)
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
         # solver handles own pinned/ctrl scratch (cudaMallocHost is slow): keep a few alive,
         # keyed on everything the handle captured by pointer
         key = (id(graph), spec.kind, spec.flags, spec.H, method_id, desc.W, desc.b, tuple(spec.p),
-               ws.data_ptr(), spec.callback is not None)
+               ws_ptr, spec.callback is not None)
         entry = _SOLVERS.get(key)
         if entry is None or spec.callback is not None:
             handle = C.c_void_p()
-            _ffi.check(lib.ndcn_solver_create(graph.handle, C.byref(desc), method_id, ws.data_ptr(), ws.numel(),
+            _ffi.check(lib.ndcn_solver_create(graph.handle, C.byref(desc), method_id, ws_ptr, ws_bytes,
                                               C.byref(handle)), "ndcn_solver_create")
+            if peers is not None:
+                cfg = peers.peer_config()
+                _ffi.check(lib.ndcn_solver_set_peers(handle, C.byref(cfg)), "ndcn_solver_set_peers")
             if len(_SOLVERS) >= 8:
                 _, (old, _g) = _SOLVERS.popitem()
                 lib.ndcn_solver_destroy(old)
@@ -238,6 +253,8 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
         finally:
             if spec.callback is not None:
                 lib.ndcn_solver_destroy(handle)
+    if peers is not None:
+        peers.n_solves += 1
     last_solve_info = SolveInfo(stats.nfe, stats.n_accepted, stats.n_rejected, stats.n_launches, stats.first_step,
                                 stats.last_dt, stats.t_final, stats.status, tuple(stats.class_ms),
                                 tuple(stats.class_launches))

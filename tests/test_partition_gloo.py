@@ -140,3 +140,34 @@ def test_exchange_volumes_prefers_feature_sharding_without_locality():
     v = partition.exchange_volumes(grid, 8, 256)
     assert v["halo"] < v["feature"]           # a grid block needs one line of nodes from each neighbour
     assert partition.exchange_volumes(grid, 3, 256)["feature"] is None
+
+
+# ---- peer-push scheme: host-side index logic (no device, no process group) -------------------
+@pytest.mark.parametrize("world,n", [(2, 257), (3, 100), (4, 64), (8, 1001)])
+def test_full_halo_layout_and_push_offsets(world, n):
+    """Every rank 'pushes' its block into every peer's buffer at halo_row_offset(); afterwards each
+    rank's buffer must be [own rows | remote rows in global order] and its local CSR applied to that
+    buffer must give its rows of Phi x -- the arithmetic PushPartition.peer_config() does in bytes."""
+    H = 4
+    phi = wl.graph_operator(wl.power_law_adjacency(n, 3, seed=2), "norm_lap")
+    x = np.random.RandomState(1).standard_normal((n, H)).astype(np.float32)
+    blocks = [partition.build_local_block(phi, world, r, full_halo=True) for r in range(world)]
+    bounds = blocks[0].bounds
+    bufs = [np.full((n, H), np.nan, np.float32) for _ in range(world)]
+    for src in range(world):
+        r0, r1 = int(bounds[src]), int(bounds[src + 1])
+        bufs[src][:r1 - r0] = x[r0:r1]
+        for dst in range(world):
+            if dst != src:
+                off = partition.halo_row_offset(bounds, src, dst)
+                assert np.isnan(bufs[dst][off:off + (r1 - r0)]).all()  # blocks never overlap
+                bufs[dst][off:off + (r1 - r0)] = x[r0:r1]
+    ref = phi @ x
+    for r, blk in enumerate(blocks):
+        assert blk.n_local + blk.n_halo == n
+        assert not np.isnan(bufs[r]).any()
+        assert np.array_equal(bufs[r][blk.n_local:], x[blk.halo_global])
+        local = sp.csr_matrix((blk.val, blk.col, blk.rowptr), shape=(blk.n_local, n))
+        assert np.allclose(local @ bufs[r], ref[int(bounds[r]):int(bounds[r + 1])], rtol=1e-5, atol=1e-6)
+    vols = partition.exchange_volumes(phi, world, H)
+    assert vols["push"] == (world - 1) * blocks[0].n_local * H * 4
