@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--exchange", choices=["auto", "halo", "feature", "push"], default="auto",
                     help="multi-GPU exchange scheme: halo rows of the row partition, feature-sharded gather, "
                          "or whichever moves fewer bytes per RHS (auto)")
+    ap.add_argument("--even-rows", action="store_true",
+                    help="multi-GPU push: equal row counts per rank instead of cost-balanced row blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds for the cpu_baseline sample")
@@ -327,7 +329,12 @@ def main_ours(args):
             # peer push needs CUDA IPC between the ranks' processes; agree collectively whether it came up
             ok = torch.ones(1, device=dev)
             try:
-                part = partition.PushPartition.build(phi, world, rank, dev, H, args.method if not args.adaptive else "dopri5")
+                # rows per rank balanced by cost: 0.16 ns per gathered entry; per row the larger of the stage
+                # kernel's own time (2.0 ns) and the NVLink push of (P-1) KB at ~750 GB/s
+                row_ns = max(2.0, 1.37 * (world - 1) * H / 256.0)
+                bounds = None if args.even_rows else partition.cost_balanced_blocks(phi, world, row_ns / 0.16)
+                part = partition.PushPartition.build(phi, world, rank, dev, H,
+                                                     args.method if not args.adaptive else "dopri5", bounds=bounds)
             except Exception as exc:  # pragma: no cover - depends on the box
                 print("rank %d: peer push unavailable (%s); falling back" % (rank, exc), file=sys.stderr)
                 ok.zero_()
@@ -448,7 +455,8 @@ def main_ours(args):
         "share_of_step": (stage_ms + gather_ms) / ms if ms > 0 else None,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
         "class_ms": {"stage": stage_ms, "gather": gather_ms, "algebra": info.class_ms[_ffi.K_ALGEBRA],
-                     "control": info.class_ms[_ffi.K_CONTROL], "emit": info.class_ms[_ffi.K_EMIT]},
+                     "control": info.class_ms[_ffi.K_CONTROL], "emit": info.class_ms[_ffi.K_EMIT],
+                     "exchange": info.class_ms[_ffi.K_EXCHANGE]},
         "per_kernel": {
             "gemm_epilogue": {"avg_ms": stage_ms / max(stage_n, 1), "launches": int(stage_n)},
             "gather": {"avg_ms": gather_ms / max(gather_n, 1), "launches": int(gather_n),

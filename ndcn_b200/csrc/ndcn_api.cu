@@ -961,11 +961,18 @@ struct Driver : StageTimer {
     return o->exchange(o->exchange_user, 1, sv->xchg);
   }
 
-  // gather source `buf` -> also into the halo region of every peer (peer push: initial state)
-  int push_copy(float* buf) {
-    for (int j = 0; j < sv->n_push; ++j)
-      CU_TRY(cudaMemcpyAsync((char*)buf + sv->push_delta[j], buf, sizeof(float) * (size_t)sv->numel, cudaMemcpyDefault, st));
-    return 0;
+  // initial state -> own rows of gather source `dst` (and, peer push, the same rows at every peer)
+  int put_y0(float* dst, const float* y0) {
+    if (!push()) {
+      CU_TRY(cudaMemcpyAsync(dst, y0, sizeof(float) * (size_t)sv->numel, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
+    PushDeltas pd;
+    pd.n = sv->n_push;
+    for (int j = 0; j < kMaxPeers; ++j) pd.delta[j] = j < sv->n_push ? sv->push_delta[j] : 0;
+    sv->launches += 1;
+    k_copy_push<<<grid_for_elems(sv->numel, sv->sm_count), kStageThreads, 0, st>>>(y0, dst, sv->numel, pd, vec_ok ? 1 : 0);
+    return (int)cudaGetLastError();
   }
 
   int exchange(float* buf) {  // make the halo rows of a gather source valid (multi-GPU)
@@ -1057,8 +1064,7 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
     cur = out;
   } else {
     if (d.push()) RC_TRY(d.peer_barrier(nullptr));
-    CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
-    RC_TRY(d.push_copy(sv->Y[0]));
+    RC_TRY(d.put_y0(sv->Y[0], y0));
     if (!terminal) RC_TRY(d.put_state(out, 0, y0));
     cur = sv->Y[0];
   }
@@ -1266,8 +1272,7 @@ struct Dopri {
 
     // peer push: nobody may still be reading the halo rows of an earlier solve when y0 arrives
     if (d.push()) RC_TRY(d.peer_barrier(nullptr));
-    CU_TRY(cudaMemcpyAsync(sv->Y[0], y0, bytes, cudaMemcpyDeviceToDevice, st));
-    RC_TRY(d.push_copy(sv->Y[0]));
+    RC_TRY(d.put_y0(sv->Y[0], y0));
     if (!terminal) RC_TRY(d.put_state(out, 0, y0));
 
     emit.ctrl = sv->ctrl;

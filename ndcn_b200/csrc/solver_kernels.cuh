@@ -112,6 +112,32 @@ __global__ void __launch_bounds__(32) k_peer_barrier(PeerArgs a, double* payload
   }
 }
 
+// initial state of a peer-push solve: dst (own rows of the gather source) and the same rows in every
+// peer's buffer, through the same store path as every later push
+struct PushDeltas {
+  int n;
+  long long delta[kMaxPeers];  // bytes
+};
+__global__ void __launch_bounds__(kStageThreads) k_copy_push(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int64_t numel, PushDeltas pd, int vec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = vec ? (numel >> 2) : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = v;
+#pragma unroll
+    for (int j = 0; j < kMaxPeers; ++j)
+      if (j < pd.n) *reinterpret_cast<float4*>(reinterpret_cast<char*>(dst + i * 4) + pd.delta[j]) = v;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const float v = src[i];
+    dst[i] = v;
+#pragma unroll
+    for (int j = 0; j < kMaxPeers; ++j)
+      if (j < pd.n) *reinterpret_cast<float*>(reinterpret_cast<char*>(dst + i) + pd.delta[j]) = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Accept / reject + next step size.  One block; thread 0 does the float64 scalar work.
 // `reduce_stage`: 0 = sum partials and (single GPU) decide immediately;

@@ -54,6 +54,29 @@ def row_blocks(n: int, world: int) -> np.ndarray:
     return np.concatenate([[0], np.cumsum(sizes)])
 
 
+def cost_balanced_blocks(phi, world: int, edges_per_row: float = 12.5, align: int = 128) -> np.ndarray:
+    """Block boundaries [world + 1] that equalise the per-rank cost of one RHS evaluation instead of the
+    row count.  The gather costs time per stored entry of Phi, the GEMM / stage algebra / push per row;
+    with ``edges_per_row`` = (time per row) / (time per entry) a row weighs ``deg + edges_per_row``
+    (measured on B200 at H=256: 0.16 ns per gathered entry, 2.0 ns per row -> 12.5).  On a power-law graph
+    in generation order the first rows are the hubs: an even split at P=2 leaves 70 % of the entries on
+    rank 0.  Cuts are rounded to ``align`` rows (whole tcgen05 tiles) where that keeps every block non-empty."""
+    phi = phi.tocsr()
+    n = phi.shape[0]
+    if world <= 1:
+        return np.array([0, n], np.int64)
+    cost = np.diff(phi.indptr).astype(np.float64) + float(edges_per_row)
+    cum = np.cumsum(cost)
+    cuts = []
+    for r in range(1, world):
+        c = int(np.searchsorted(cum, cum[-1] * r / world)) + 1
+        if align > 1 and n >= 4 * align * world:
+            c = int(round(c / align)) * align
+        lo = (cuts[-1] if cuts else 0) + 1
+        cuts.append(min(max(c, lo), n - (world - r)))
+    return np.array([0] + cuts + [n], np.int64)
+
+
 @dataclass
 class LocalBlock:
     """Host-side description of one rank's share (pure numpy; no device, no process group)."""
@@ -87,12 +110,15 @@ def halo_row_offset(bounds: np.ndarray, src_rank: int, dst_rank: int) -> int:
     return row0_src + (n_local_dst if src_rank < dst_rank else 0)
 
 
-def build_local_block(phi, world: int, rank: int, full_halo: bool = False) -> LocalBlock:
+def build_local_block(phi, world: int, rank: int, full_halo: bool = False,
+                      bounds: Optional[np.ndarray] = None) -> LocalBlock:
     """Slice rows [row0,row1) of the scipy CSR operator and remap its columns.  ``full_halo``: the halo
-    is EVERY remote row, referenced or not (peer-push scheme: remote blocks arrive whole)."""
+    is EVERY remote row, referenced or not (peer-push scheme: remote blocks arrive whole).  ``bounds``:
+    block boundaries [world + 1] (default: even row counts, ``row_blocks``)."""
     phi = phi.tocsr()
     n = phi.shape[0]
-    bounds = row_blocks(n, world)
+    bounds = row_blocks(n, world) if bounds is None else np.asarray(bounds, np.int64)
+    assert len(bounds) == world + 1 and bounds[0] == 0 and bounds[-1] == n and bool((np.diff(bounds) > 0).all())
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     blk = phi[r0:r1].tocsr()
     blk.sort_indices()
@@ -154,8 +180,9 @@ class RowPartition:
         return t.to(self.device) if self.device.type == "cuda" else t
 
     @classmethod
-    def build(cls, phi, world: int, rank: int, device: torch.device, H: int, group=None) -> "RowPartition":
-        return cls(build_local_block(phi, world, rank), device, H, group)
+    def build(cls, phi, world: int, rank: int, device: torch.device, H: int, group=None,
+              bounds: Optional[np.ndarray] = None) -> "RowPartition":
+        return cls(build_local_block(phi, world, rank, bounds=bounds), device, H, group)
 
     # ------------------------------------------------------------------------------------
     def fill_halo(self, buf: torch.Tensor) -> None:
@@ -330,12 +357,13 @@ class PushPartition:
     # ---- construction ----------------------------------------------------------------------
     @classmethod
     def build(cls, phi, world: int, rank: int, device: torch.device, H: int, method: str = "dopri5",
-              group=None) -> "PushPartition":
+              group=None, bounds: Optional[np.ndarray] = None) -> "PushPartition":
         """One process per GPU: exchange the 64-byte IPC handles through the process group and map the
-        peers (``cudaIpcOpenMemHandle``; the peers' GPUs must be reachable over NVLink / PCIe P2P)."""
+        peers (``cudaIpcOpenMemHandle``; the peers' GPUs must be reachable over NVLink / PCIe P2P).
+        ``bounds``: row-block boundaries, e.g. ``cost_balanced_blocks(phi, world)``."""
         import torch.distributed as dist
 
-        self = cls(build_local_block(phi, world, rank, full_halo=True), device, H, method)
+        self = cls(build_local_block(phi, world, rank, full_halo=True, bounds=bounds), device, H, method)
         handles: List[Optional[bytes]] = [None] * world
         dist.all_gather_object(handles, bytes(self._handle.raw), group=group)
         lib = _ffi.lib()
@@ -352,9 +380,10 @@ class PushPartition:
         return self
 
     @classmethod
-    def build_in_process(cls, phi, world: int, devices, H: int, method: str = "dopri5") -> List["PushPartition"]:
+    def build_in_process(cls, phi, world: int, devices, H: int, method: str = "dopri5",
+                         bounds: Optional[np.ndarray] = None) -> List["PushPartition"]:
         """All ranks inside one process (tests): rank r lives on ``devices[r]`` (the same GPU is fine)."""
-        parts = [cls(build_local_block(phi, world, r, full_halo=True), torch.device(devices[r]), H, method)
+        parts = [cls(build_local_block(phi, world, r, full_halo=True, bounds=bounds), torch.device(devices[r]), H, method)
                  for r in range(world)]
         lib = _ffi.lib()
         for a in parts:
@@ -384,7 +413,8 @@ class PushPartition:
 
     def describe(self) -> dict:
         return {"scheme": "peer push (stage-kernel stores into IPC-mapped peer buffers + device barrier)",
-                "rows_local": self.n_local, "halo_rows": self.n_halo,
+                "rows_local": self.n_local, "halo_rows": self.n_halo, "nnz_local": int(len(self.block.col)),
+                "row_bounds": [int(b) for b in self.bounds],
                 "push_bytes_per_rhs": (self.world - 1) * self.n_local * self.H * 4, "solves": self.n_solves}
 
     def close(self, group=None) -> None:

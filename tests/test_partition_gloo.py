@@ -171,3 +171,40 @@ def test_full_halo_layout_and_push_offsets(world, n):
         assert np.allclose(local @ bufs[r], ref[int(bounds[r]):int(bounds[r + 1])], rtol=1e-5, atol=1e-6)
     vols = partition.exchange_volumes(phi, world, H)
     assert vols["push"] == (world - 1) * blocks[0].n_local * H * 4
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_cost_balanced_blocks(world):
+    """Power-law graph in generation order: the hubs come first, so equal row counts leave most of the
+    gather work on rank 0; the cost-balanced cuts must cover all rows, stay ordered, lower the maximum
+    cost, and the full-halo push layout must hold for ragged blocks."""
+    n, H = 40000, 4
+    phi = wl.graph_operator(wl.power_law_adjacency(n, 5, seed=3), "norm_lap")
+    epr = 12.5
+    even = partition.row_blocks(n, world)
+    bal = partition.cost_balanced_blocks(phi, world, epr)
+    assert bal[0] == 0 and bal[-1] == n and len(bal) == world + 1 and (np.diff(bal) > 0).all()
+    assert all(int(b) % 128 == 0 for b in bal[1:-1])
+
+    def max_cost(b):
+        return max((phi.indptr[b[i + 1]] - phi.indptr[b[i]]) + epr * (b[i + 1] - b[i]) for i in range(world))
+
+    assert max_cost(bal) < 0.95 * max_cost(even)
+    assert max_cost(bal) < 1.02 * (phi.nnz + epr * n) / world
+    # tiny graphs: no alignment, still a valid partition
+    small = wl.graph_operator(wl.power_law_adjacency(50, 3, seed=1), "norm_lap")
+    bs = partition.cost_balanced_blocks(small, world)
+    assert bs[0] == 0 and bs[-1] == 50 and (np.diff(bs) > 0).all()
+    # ragged full-halo layout
+    x = np.random.RandomState(0).standard_normal((n, H)).astype(np.float32)
+    ref = phi @ x
+    for r in (0, world - 1):
+        blk = partition.build_local_block(phi, world, r, full_halo=True, bounds=bal)
+        buf = np.empty((n, H), np.float32)
+        buf[:blk.n_local] = x[bal[r]:bal[r + 1]]
+        for src in range(world):
+            if src != r:
+                off = partition.halo_row_offset(bal, src, r)
+                buf[off:off + (bal[src + 1] - bal[src])] = x[bal[src]:bal[src + 1]]
+        local = sp.csr_matrix((blk.val, blk.col, blk.rowptr), shape=(blk.n_local, n))
+        assert np.allclose(local @ buf, ref[bal[r]:bal[r + 1]], rtol=1e-5, atol=1e-6)
