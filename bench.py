@@ -41,8 +41,11 @@ T_TOTAL, STEPS_TOTAL = 5.0, 100  # north star: T=5, 100 dopri5 steps  ->  dt = 0
 DT = T_TOTAL / STEPS_TOTAL
 
 
-PUSH_MAX_WORLD = 4  # above this the feature-sharded gather moves far fewer bytes than the push
-PUSH_IN_AUTO = False  # `--exchange auto` may pick the peer-push scheme (switched on once measured on the box)
+# measured on the 1M-node power-law graph (profiles/README.md): push 12.8 / 11.1 ms per step at 2 / 4 GPUs against
+# 18.7 (halo) / 12.3 (feature); at 8 GPUs every rank would receive 875 MB per RHS over NVLink (>= 1.2 ms), the
+# feature-sharded gather moves 224 MB and measured 7.2 ms per step
+PUSH_MAX_WORLD = 4
+PUSH_IN_AUTO = True  # `--exchange auto` may pick the peer-push scheme
 
 
 def parse_args():
@@ -539,6 +542,9 @@ def main_ours(args):
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line))
+    if peers is not None:
+        solver.release_workspaces()  # solver handles point into the IPC-shared workspace
+        peers.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
