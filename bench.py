@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--adaptive", action="store_true",
                     help="dopri5 with the NDCN tolerances (rtol .01, atol .001) over T=5 instead of forced steps; "
                          "reports the measured accepted/rejected steps (SURVEY.md section 8(d)); single GPU")
-    ap.add_argument("--exchange", choices=["auto", "halo", "feature", "push"], default="auto",
+    ap.add_argument("--exchange", choices=["auto", "halo", "feature", "push", "fpush"], default="auto",
                     help="multi-GPU exchange scheme: halo rows of the row partition, feature-sharded gather, "
                          "or whichever moves fewer bytes per RHS (auto)")
     ap.add_argument("--even-rows", action="store_true",
@@ -328,16 +328,19 @@ def main_ours(args):
         if scheme == "auto":
             scheme = pick_exchange(vols, world, H)
         peers = None
-        if scheme == "push":
+        if scheme in ("push", "fpush"):
             # peer push needs CUDA IPC between the ranks' processes; agree collectively whether it came up
             ok = torch.ones(1, device=dev)
+            meth = args.method if not args.adaptive else "dopri5"
             try:
-                # rows per rank balanced by cost: 0.16 ns per gathered entry; per row the larger of the stage
-                # kernel's own time (2.0 ns) and the NVLink push of (P-1) KB at ~750 GB/s
-                row_ns = max(2.0, 1.37 * (world - 1) * H / 256.0)
-                bounds = None if args.even_rows else partition.cost_balanced_blocks(phi, world, row_ns / 0.16)
-                part = partition.PushPartition.build(phi, world, rank, dev, H,
-                                                     args.method if not args.adaptive else "dopri5", bounds=bounds)
+                if scheme == "fpush":
+                    part = partition.FeaturePushPartition.build(phi, world, rank, dev, H, meth)
+                else:
+                    # rows per rank balanced by cost: 0.16 ns per gathered entry; per row the larger of the stage
+                    # kernel's own time (2.0 ns) and the NVLink push of (P-1) KB at ~750 GB/s
+                    row_ns = max(2.0, 1.37 * (world - 1) * H / 256.0)
+                    bounds = None if args.even_rows else partition.cost_balanced_blocks(phi, world, row_ns / 0.16)
+                    part = partition.PushPartition.build(phi, world, rank, dev, H, meth, bounds=bounds)
             except Exception as exc:  # pragma: no cover - depends on the box
                 print("rank %d: peer push unavailable (%s); falling back" % (rank, exc), file=sys.stderr)
                 ok.zero_()
@@ -346,12 +349,12 @@ def main_ours(args):
             if float(ok.item()) < 1.0:
                 if part is not None:
                     part.close(group=False)
-                if args.exchange == "push":
-                    raise RuntimeError("--exchange push: CUDA IPC peer mapping failed on some rank")
+                if args.exchange in ("push", "fpush"):
+                    raise RuntimeError("--exchange %s: CUDA IPC peer mapping failed on some rank" % args.exchange)
                 scheme = pick_exchange(vols, world, H, allow_push=False)
             else:
                 peers = part
-        if scheme == "push":
+        if scheme in ("push", "fpush"):
             pass
         elif scheme == "feature":
             part = partition.FeaturePartition(phi, world, rank, dev, H)
@@ -424,7 +427,8 @@ def main_ours(args):
     gather_n = info.class_launches[_ffi.K_GATHER]
     rhs_avg_ms = (stage_ms + gather_ms) / max(stage_n, 1)
     n_rows_local = graph.n_rows
-    nnz_local = graph.nnz if not z_block_cols else nnz // world  # feature-sharded: every rank gathers all rows on 1/world of the columns
+    slice_cols = z_block_cols or (part.Hc if (world > 1 and scheme == "fpush") else 0)
+    nnz_local = graph.nnz if not slice_cols else nnz // world  # feature-sharded: every rank gathers all rows on 1/world of the columns
     algo_bytes = bytes_rhs(n_rows_local, nnz_local, H)
     peaks = {}
     try:
@@ -443,7 +447,7 @@ def main_ours(args):
     split = gather_n > 0
     # which gather the library's auto rule picks (csrc/ndcn_api.cu::pick_gather_cw)
     cw_cfg = int(_ffi.lib().ndcn_config_get(_ffi.CFG_GATHER_CW))
-    Hg = z_block_cols or H
+    Hg = slice_cols or H
     slab_fits = Hg > 32 and graph.n_cols * Hg * 4 > (64 << 20) and graph.n_cols * 128 <= (48 << 20)
     chunked = cw_cfg > 0 or (cw_cfg == 0 and (slab_fits or (Hg <= 64 and graph.n_cols >= 4096)))
     gather_name = ("chunk-major CSR gather (k_stage_gather_chunk)" if chunked
@@ -523,7 +527,12 @@ def main_ours(args):
         "solver": {"nfe": info.nfe, "accepted": info.n_accepted, "rejected": info.n_rejected, "finite": finite},
     }
     if world > 1:
-        if peers is not None:
+        if peers is not None and scheme == "fpush":
+            line["config"]["parallelism"] = ("1-D node-row partition x%d for the state / GEMM / solver algebra, feature-sharded "
+                                             "gather over peer memory: stage epilogues scatter column slices into the "
+                                             "IPC-mapped slice buffers of all ranks, the slice gather stores z into the "
+                                             "row owners' Z, 2 device barrier kernels per RHS eval, no NCCL on the path" % world)
+        elif peers is not None:
             line["config"]["parallelism"] = ("1-D node-row partition x%d, peer push: stage kernels store new rows into "
                                              "the IPC-mapped gather sources of all peers (NVLink), device barrier "
                                              "kernel per RHS eval, no NCCL on the path" % world)

@@ -221,6 +221,28 @@ typedef struct ndcn_peer_config {
   int64_t delta_bytes[8];   /* entry `rank` ignored */
 } ndcn_peer_config_t;
 int ndcn_solver_set_peers(ndcn_solver_t* sv, const ndcn_peer_config_t* cfg /* NULL: off */);
+/* Feature-sharded peer push: the exchange volume of the feature-sharded gather (2 (P-1)/P^2 of the state
+ * per RHS and rank instead of (P-1)/P for any all-gather) with the push mechanism instead of two NCCL
+ * all-to-alls.  The state, the tcgen05 GEMM and the solver algebra stay row-sharded; rank q additionally
+ * owns the column slice [q Hc, (q+1) Hc), Hc = H / world, of EVERY node:
+ *   - every kernel that produces a gather source scatters each new row, slice by slice, into the slice
+ *     buffers xcs[q] ([N, Hc], rows in global order) of all ranks;
+ *   - barrier; every rank gathers ALL rows of `full_graph` on its own slice and stores z = Phi x straight
+ *     into block `rank` of the blocked Z ([world][n_local_o][Hc]) of the rank o that owns the row;
+ *   - barrier; the tcgen05 stage kernel reads that blocked Z (as with NDCN_GATHER_EXTERNAL).
+ * The solver is created on a graph handle with n_rows = n_cols = n_local and no entries (it never
+ * gathers itself).  NDCN right-hand sides with W, H in {128, 256}, H / world a power of two >= 32.
+ *   pad[r], xcs[r], z[r]  addresses (in THIS process) of rank r's signal pad / slice buffer / blocked Z
+ *   row_bounds            block boundaries [world + 1]; rank r owns rows [row_bounds[r], row_bounds[r+1])  */
+typedef struct ndcn_feature_peer_config {
+  int32_t rank, world;
+  void* pad[8];
+  void* xcs[8];
+  void* z[8];
+  int64_t row_bounds[9];
+} ndcn_feature_peer_config_t;
+int ndcn_solver_set_feature_peers(ndcn_solver_t* sv, const ndcn_graph_t* full_graph,
+                                  const ndcn_feature_peer_config_t* cfg /* NULL: off */);
 /* cudaMalloc + cudaIpcGetMemHandle (64-byte handle); the first 4 KB are zeroed (signal pad) */
 int ndcn_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
 int ndcn_peer_open(const unsigned char* handle, void** ptr_out); /* cudaIpcOpenMemHandle */

@@ -60,6 +60,13 @@ class PeerConfig(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("pad", C.c_void_p * 8), ("delta_bytes", C.c_int64 * 8)]
 
 
+class FeaturePeerConfig(C.Structure):
+    """``ndcn_feature_peer_config_t``: feature-sharded peer push (partition.FeaturePushPartition)."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("pad", C.c_void_p * 8), ("xcs", C.c_void_p * 8),
+                ("z", C.c_void_p * 8), ("row_bounds", C.c_int64 * 9)]
+
+
 class GatherRequest(C.Structure):
     _fields_ = [("src_dev", C.c_void_p), ("z_dev", C.c_void_p)]
 
@@ -95,6 +102,7 @@ PROTOTYPES = {
     "ndcn_pack_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_pack_cols_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_solver_set_peers": (C.c_int, [C.c_void_p, C.POINTER(PeerConfig)]),
+    "ndcn_solver_set_feature_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(FeaturePeerConfig)]),
     "ndcn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "ndcn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "ndcn_peer_close": (C.c_int, [C.c_void_p]),

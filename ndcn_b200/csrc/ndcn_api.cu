@@ -131,6 +131,14 @@ static void keep_scratch_pooled() {
   }
 }
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+static inline int ilog2(int64_t v) {
+  int l = 0;
+  while (v > 1) {
+    v >>= 1;
+    ++l;
+  }
+  return l;
+}
 static inline PtrPair pp(float* a) { return PtrPair{{a, a}}; }
 static inline PtrPair pp(float* a, float* b) { return PtrPair{{a, b}}; }
 
@@ -165,6 +173,14 @@ struct ndcn_solver {
   PeerArgs peers{};
   int n_push = 0;                      // world - 1
   long long push_delta[kMaxPeers] = {};  // byte distance local gather-source element -> the same element at peer j
+  // feature-sharded peer push (ndcn_solver_set_feature_peers)
+  bool feat_on = false;
+  FeatTable* feat_dev = nullptr;       // library-owned copy of the pointer table
+  const ndcn_graph* full_graph = nullptr;
+  float* xcs_self = nullptr;           // this rank's slice buffer [N, Hc]
+  float* Z_own = nullptr;              // workspace Z, restored when the scheme is switched off
+  int feat_rank = 0, feat_world = 0, feat_hc = 0;
+  int feat_bounds[9] = {};
 };
 
 // ---------------------------------------------------------------------------------------
@@ -309,7 +325,7 @@ static int launch_gather(const RhsBinding& b, const NdcnArgs& a, int H, EpiArgs&
       default: return launch_ndcn_fast<1, 1>(a2, e, grid_out, st);
     }
   }
-  if (gather_uses_v2(cw, a.flags)) {
+  if (gather_uses_v2(cw, a.flags) && e.feat_mode != FEAT_Z_OWNERS) {
     const int n_blocks = (int)((a.g.n_rows + kG2Rows - 1) / kG2Rows);
     const int64_t total = (int64_t)(H / cw) * (n_blocks + b.g->n_long);
     const bool store_only = e.mode == EPI_STORE;
@@ -875,6 +891,7 @@ extern "C" int ndcn_solver_destroy(ndcn_solver_t* sv) {
   if (sv->t_stage) cudaFree(sv->t_stage);
   if (sv->t_out) cudaFree(sv->t_out);
   if (sv->ctrl) cudaFree(sv->ctrl);
+  if (sv->feat_dev) cudaFree(sv->feat_dev);
   if (sv->ctrl_host) cudaFreeHost(sv->ctrl_host);
   delete sv;
   return NDCN_OK;
@@ -933,15 +950,27 @@ struct Driver : StageTimer {
     evs.clear();
   }
 
-  bool push() const { return sv->n_push > 0; }
+  bool feat() const { return sv->feat_on; }
+  bool push() const { return sv->n_push > 0 || sv->feat_on; }  // peers reached through mapped memory + device barriers
   bool multi() const { return o->exchange != nullptr || push(); }
 
+  void fill_feat(EpiArgs& e, int mode) const {
+    e.feat = sv->feat_dev;
+    e.feat_mode = mode;
+    e.feat_rank = sv->feat_rank;
+    e.feat_row0 = sv->feat_bounds[sv->feat_rank];
+    e.feat_hc_log2 = ilog2(sv->feat_hc);
+    e.feat_h_log2 = ilog2(sv->H);
+  }
+
   // every y_out of a solve is a gather source: on a peer-push solve it is also stored at the peers
+  // (whole rows at a byte delta, or -- feature-sharded -- column slice by column slice)
   EpiArgs blank() const {
     EpiArgs e;
     std::memset(&e, 0, sizeof(e));
     e.n_peers = sv->n_push;
     for (int j = 0; j < sv->n_push; ++j) e.peer_delta[j] = sv->push_delta[j];
+    if (sv->feat_on) fill_feat(e, FEAT_Y_SLICES);
     return e;
   }
 
@@ -967,6 +996,12 @@ struct Driver : StageTimer {
       CU_TRY(cudaMemcpyAsync(dst, y0, sizeof(float) * (size_t)sv->numel, cudaMemcpyDeviceToDevice, st));
       return 0;
     }
+    if (feat()) {
+      sv->launches += 1;
+      k_copy_slices<<<grid_for_elems(sv->numel, sv->sm_count), kStageThreads, 0, st>>>(
+          y0, dst, sv->numel, sv->feat_dev, sv->feat_bounds[sv->feat_rank], ilog2(sv->H), ilog2(sv->feat_hc));
+      return (int)cudaGetLastError();
+    }
     PushDeltas pd;
     pd.n = sv->n_push;
     for (int j = 0; j < kMaxPeers; ++j) pd.delta[j] = j < sv->n_push ? sv->push_delta[j] : 0;
@@ -976,6 +1011,7 @@ struct Driver : StageTimer {
   }
 
   int exchange(float* buf) {  // make the halo rows of a gather source valid (multi-GPU)
+    if (feat()) return 0;  // stage() brackets the slice gather with its own barriers
     if (push()) return peer_barrier(nullptr);
     if (o->exchange && sv->n_cols > sv->n_rows) return o->exchange(o->exchange_user, 0, buf);
     return 0;
@@ -998,6 +1034,30 @@ struct Driver : StageTimer {
       if (rc != 0) return rc;
       RhsBinding b2 = bind;
       b2.z_block_cols = o->z_block_cols;
+      return launch_stage(b2, src, e, n_partials, st);
+    }
+    if (feat()) {
+      // feature-sharded peer push: the producers of `src` have scattered it into every rank's slice buffer;
+      // gather ALL rows on the own slice, storing z into the owners' blocked Z, then the tcgen05 stage kernel
+      nfe += 1;
+      RC_TRY(peer_barrier(nullptr));  // slices complete
+      ndcn_rhs_desc_t rg;
+      std::memset(&rg, 0, sizeof(rg));
+      rg.kind = NDCN_RHS_NDCN;
+      rg.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+      rg.H = sv->feat_hc;
+      RhsBinding bg{sv->full_graph, &rg, nullptr, nullptr, 0, sv->sm_count};
+      bg.launches = &sv->launches;
+      EpiArgs se = store_only(nullptr);
+      se.ctrl = e.ctrl;
+      fill_feat(se, FEAT_Z_OWNERS);
+      t_begin(NDCN_K_GATHER);
+      const int rcg = launch_stage(bg, pp(sv->xcs_self), se, nullptr, st);
+      t_end();
+      if (rcg != 0) return rcg;
+      RC_TRY(peer_barrier(nullptr));  // every block of Z has arrived
+      RhsBinding b2 = bind;
+      b2.z_block_cols = sv->feat_hc;
       return launch_stage(b2, src, e, n_partials, st);
     }
     RC_TRY(exchange(src_host));
@@ -1055,7 +1115,7 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
   ndcn_solver* sv = d.sv;
   cudaStream_t st = d.st;
   const bool terminal = (d.o->flags & NDCN_O_TERMINAL_ONLY) != 0;
-  const bool multi = sv->n_cols > sv->n_rows;
+  const bool multi = sv->n_cols > sv->n_rows || d.push();
   const bool in_slab = !terminal && !multi && !d.decoding();  // the output slab doubles as state storage
   const size_t bytes = sizeof(float) * (size_t)sv->numel;
   float* cur;
@@ -1225,7 +1285,6 @@ struct Dopri {
     cudaStream_t st = d.st;
     const bool terminal = (d.o->flags & NDCN_O_TERMINAL_ONLY) != 0;
     const bool forced = (d.o->flags & NDCN_O_FORCED_DT) != 0;
-    const size_t bytes = sizeof(float) * (size_t)sv->numel;
     host_parity = d.o->exchange != nullptr || sv->rhs.kind == NDCN_RHS_CALLBACK;
 
     // requested times -> device (float64, already fp32-rounded by ODEBlock when it applies)
@@ -1256,7 +1315,9 @@ struct Dopri {
     h.n_out = n_t;
     h.emit_lo = h.emit_hi = 1;
     h.terminal_only = terminal ? 1 : 0;
-    if (d.push()) {
+    if (d.feat()) {
+      h.numel_global = (double)sv->feat_bounds[sv->feat_world] * (double)sv->H;
+    } else if (d.push()) {
       h.numel_global = (double)sv->n_cols * (double)sv->H;  // full halo: n_cols = all nodes
     } else if (d.o->exchange) {
       // global element count = all-reduce of the local one (same hook, what = 1)
@@ -1375,7 +1436,8 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   if (sv->rhs.kind == NDCN_RHS_NDCN && fast_h && !(aligned16(out) && aligned16(y0))) return NDCN_E_ARG;
   if (opts->gather_mode != NDCN_GATHER_LOCAL && opts->gather_mode != NDCN_GATHER_EXTERNAL) return NDCN_E_ARG;
   if (opts->dec_classes < 0 || opts->dec_classes > kDecMaxC || (opts->dec_classes > 0 && !opts->dec_W)) return NDCN_E_ARG;
-  const bool external = opts->gather_mode == NDCN_GATHER_EXTERNAL;
+  const bool external = opts->gather_mode == NDCN_GATHER_EXTERNAL || sv->feat_on;
+  if (sv->feat_on && (opts->gather_mode != NDCN_GATHER_LOCAL || opts->exchange)) return NDCN_E_ARG;
   if (external && !(umma_eligible(sv->rhs, ((int64_t)1) << 40) && sv->Wimg && sv->Z)) return NDCN_E_ARG;
   if ((external || umma_eligible(sv->rhs, sv->n_rows)) && sv->Wimg) {
     if (sv->H == 256) prep_w_image<256>(sv->rhs.W, sv->Wimg, st);
@@ -1442,6 +1504,56 @@ extern "C" int ndcn_solver_set_peers(ndcn_solver_t* sv, const ndcn_peer_config_t
     sv->push_delta[j++] = (long long)cfg->delta_bytes[r];
   }
   sv->n_push = cfg->world - 1;
+  return NDCN_OK;
+}
+
+extern "C" int ndcn_solver_set_feature_peers(ndcn_solver_t* sv, const ndcn_graph_t* full_graph,
+                                             const ndcn_feature_peer_config_t* cfg) {
+  if (!sv) return NDCN_E_ARG;
+  if (sv->feat_on) {  // off / reconfigure: give the workspace Z back
+    sv->Z = sv->Z_own;
+    sv->feat_on = false;
+  }
+  if (!cfg || cfg->world <= 1) return NDCN_OK;
+  const int P = cfg->world;
+  if (!full_graph || P > 8 || cfg->rank < 0 || cfg->rank >= P) return NDCN_E_ARG;
+  if (sv->rhs.kind != NDCN_RHS_NDCN || (sv->rhs.flags & (NDCN_F_NO_GRAPH | NDCN_F_NO_CONTROL))) return NDCN_E_ARG;
+  if ((sv->H != 128 && sv->H != 256) || sv->H % P != 0 || !sv->Wimg || !sv->Z) return NDCN_E_ARG;
+  const int hc = sv->H / P;
+  if (hc < 32 || (hc & (hc - 1)) != 0) return NDCN_E_ARG;
+  if (sv->n_push > 0) return NDCN_E_ARG;  // one scheme at a time
+  if (cfg->row_bounds[0] != 0 || cfg->row_bounds[P] != full_graph->v.n_rows) return NDCN_E_ARG;
+  for (int r = 0; r < P; ++r) {
+    if (cfg->row_bounds[r + 1] <= cfg->row_bounds[r]) return NDCN_E_ARG;
+    if (!cfg->pad[r] || !cfg->xcs[r] || !cfg->z[r] || ((uintptr_t)cfg->xcs[r] & 15u) || ((uintptr_t)cfg->z[r] & 15u))
+      return NDCN_E_ARG;
+  }
+  if (cfg->row_bounds[cfg->rank + 1] - cfg->row_bounds[cfg->rank] != sv->n_rows) return NDCN_E_ARG;
+  if (full_graph->v.n_cols != full_graph->v.n_rows) return NDCN_E_ARG;
+  FeatTable t;
+  std::memset(&t, 0, sizeof(t));
+  for (int r = 0; r < P; ++r) {
+    t.xcs[r] = (float*)cfg->xcs[r];
+    t.z[r] = (float*)cfg->z[r];
+  }
+  for (int r = 0; r <= 8; ++r) t.bounds[r] = (int)cfg->row_bounds[r <= P ? r : P];
+  t.world = P;
+  if (!sv->feat_dev) CU_TRY(cudaMalloc((void**)&sv->feat_dev, sizeof(FeatTable)));
+  CU_TRY(cudaMemcpy(sv->feat_dev, &t, sizeof(t), cudaMemcpyHostToDevice));
+  std::memset(&sv->peers, 0, sizeof(sv->peers));
+  sv->peers.self = (PeerPad*)cfg->pad[cfg->rank];
+  sv->peers.rank = cfg->rank;
+  sv->peers.world = P;
+  for (int r = 0; r < P; ++r) sv->peers.peer[r] = (PeerPad*)cfg->pad[r];
+  for (int r = 0; r <= 8; ++r) sv->feat_bounds[r] = r <= P ? (int)cfg->row_bounds[r] : (int)cfg->row_bounds[P];
+  sv->feat_rank = cfg->rank;
+  sv->feat_world = P;
+  sv->feat_hc = hc;
+  sv->full_graph = full_graph;
+  sv->xcs_self = (float*)cfg->xcs[cfg->rank];
+  sv->Z_own = sv->Z;
+  sv->Z = (float*)cfg->z[cfg->rank];
+  sv->feat_on = true;
   return NDCN_OK;
 }
 

@@ -57,6 +57,18 @@ enum EpiMode : int {
 
 enum DtSrc : int { DT_HOST = 0, DT_CTRL = 1, DT_CTRL_H0 = 2 };
 
+// Feature-sharded peer push (ndcn_solver_set_feature_peers): device-resident pointer table, one per solver.
+// Rank q gathers ALL rows on its column slice [q Hc, (q+1) Hc): producers of a gather source scatter every
+// new row into the slice buffers of all ranks (FEAT_Y_SLICES), the slice gather stores z = Phi x straight
+// into the blocked Z of the rank that owns the row (FEAT_Z_OWNERS).
+struct FeatTable {
+  float* xcs[8];  // rank q's slice buffer [N, Hc]           (IPC-mapped)
+  float* z[8];    // rank q's Z [world][n_local_q][Hc]        (IPC-mapped)
+  int bounds[9];  // row-block boundaries of the ranks (entries past `world` repeat the last one)
+  int world;
+};
+enum FeatMode : int { FEAT_OFF = 0, FEAT_Y_SLICES = 1, FEAT_Z_OWNERS = 2 };
+
 struct EpiArgs {
   int mode;
   int n_prev;         // previous stages read from HBM (<= 6)
@@ -76,6 +88,12 @@ struct EpiArgs {
   // buffers of the other ranks, peer_delta[j] BYTES away from the local address (NVLink peer stores)
   int n_peers;
   long long peer_delta[kMaxPeers];
+  // feature-sharded peer push
+  const FeatTable* feat;
+  int feat_mode;        // FeatMode
+  int feat_rank;
+  int feat_row0;        // first global row of this rank's block
+  int feat_hc_log2, feat_h_log2;
 };
 
 struct EpiCtx {  // EpiArgs resolved against the controller, per thread
@@ -91,6 +109,8 @@ struct EpiCtx {  // EpiArgs resolved against the controller, per thread
   float rtol, atol;
   int n_peers;
   long long peer_delta[kMaxPeers];
+  const FeatTable* feat;
+  int feat_mode, feat_rank, feat_row0, feat_hc_log2, feat_h_log2;
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -136,6 +156,12 @@ __device__ __forceinline__ bool epi_resolve(const EpiArgs& a, EpiCtx& c) {
   c.n_peers = a.n_peers;
 #pragma unroll
   for (int j = 0; j < kMaxPeers; ++j) c.peer_delta[j] = a.peer_delta[j];
+  c.feat = a.feat;
+  c.feat_mode = a.feat_mode;
+  c.feat_rank = a.feat_rank;
+  c.feat_row0 = a.feat_row0;
+  c.feat_hc_log2 = a.feat_hc_log2;
+  c.feat_h_log2 = a.feat_h_log2;
   return true;
 }
 
@@ -185,6 +211,19 @@ __device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[VW])
   }
 }
 
+// feature-sharded peer push: off = row * H + col of this rank's [n_local, H] block; the VW <= 4 elements lie
+// in one column slice (Hc >= 32).  Out of line on purpose: the single-GPU epilogues keep their registers.
+template <int VW>
+__device__ __noinline__ void store_y_slices(const FeatTable* __restrict__ f, int row0, int hc_log2, int h_log2,
+                                            int64_t off, float v0, float v1, float v2, float v3) {
+  const int64_t row = off >> h_log2;
+  const int col = (int)(off & (((int64_t)1 << h_log2) - 1));
+  float* dst = f->xcs[col >> hc_log2] + (((int64_t)row0 + row) << hc_log2) + (col & ((1 << hc_log2) - 1));
+  if constexpr (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+  else if constexpr (VW == 2) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+  else *dst = v0;
+}
+
 // y_out store: the local copy and, on a peer-push multi-GPU solve, the same elements in every other
 // rank's gather-source buffer (plain stores over NVLink; ordered by the k_peer_barrier that follows)
 template <int VW>
@@ -197,6 +236,26 @@ __device__ __forceinline__ void store_y(const EpiCtx& c, int64_t off, const floa
     for (int j = 0; j < kMaxPeers; ++j)
       if (j < c.n_peers) stv<VW>(reinterpret_cast<float*>(base + c.peer_delta[j]), v);
   }
+  if (c.feat_mode == FEAT_Y_SLICES)
+    store_y_slices<VW>(c.feat, c.feat_row0, c.feat_hc_log2, c.feat_h_log2, off, v[0], v[VW > 1 ? 1 : 0], v[VW > 2 ? 2 : 0],
+                       v[VW > 3 ? 3 : 0]);
+}
+
+// slice gather (FEAT_Z_OWNERS): off = row * Hc + col with row a GLOBAL node id; the value goes to block
+// `rank` of the Z of the rank that owns the row: z_o[rank][row - row0_o][col]
+template <int VW>
+__device__ __noinline__ void store_z_owner(const FeatTable* __restrict__ f, int rank, int hc_log2, int64_t off,
+                                           float v0, float v1, float v2, float v3) {
+  const int64_t row = off >> hc_log2;
+  const int col = (int)(off & (((int64_t)1 << hc_log2) - 1));
+  int o = 0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) o += (row >= f->bounds[j] && j < f->world) ? 1 : 0;  // bounds ascend: owner = # of cuts <= row
+  const int lo = f->bounds[o], hi = f->bounds[o + 1];
+  float* dst = f->z[o] + (((int64_t)rank * (hi - lo) + (row - lo)) << hc_log2) + col;
+  if constexpr (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+  else if constexpr (VW == 2) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+  else *dst = v0;
 }
 
 // ------------------------------------------------------------------------------------
@@ -231,6 +290,8 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
     if (stream_out) stv_stream<VW>(c.k_out + off, k);
     else stv<VW>(c.k_out + off, k);
   }
+  if (c.feat_mode == FEAT_Z_OWNERS)
+    store_z_owner<VW>(c.feat, c.feat_rank, c.feat_hc_log2, off, k[0], k[VW > 1 ? 1 : 0], k[VW > 2 ? 2 : 0], k[VW > 3 ? 3 : 0]);
   if (c.mode == EPI_STORE) return;
 
   if (c.mode == EPI_LINCOMB) {

@@ -138,6 +138,24 @@ __global__ void __launch_bounds__(kStageThreads) k_copy_push(const float* __rest
   }
 }
 
+// initial state of a feature-sharded peer-push solve: dst (own [n_local, H] block, row-major) and, column
+// slice by column slice, the slice buffers of all ranks.  16-byte pieces (H % 4 == 0, all bases aligned).
+__global__ void __launch_bounds__(kStageThreads) k_copy_slices(const float* __restrict__ src, float* __restrict__ dst,
+                                                               int64_t numel, const FeatTable* __restrict__ feat, int row0,
+                                                               int h_log2, int hc_log2) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = numel >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = v;
+    const int64_t off = i * 4;
+    const int64_t row = off >> h_log2;
+    const int col = (int)(off & (((int64_t)1 << h_log2) - 1));
+    float* p = feat->xcs[col >> hc_log2] + (((int64_t)row0 + row) << hc_log2) + (col & ((1 << hc_log2) - 1));
+    *reinterpret_cast<float4*>(p) = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Accept / reject + next step size.  One block; thread 0 does the float64 scalar work.
 // `reduce_stage`: 0 = sum partials and (single GPU) decide immediately;

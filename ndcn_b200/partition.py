@@ -20,6 +20,10 @@ whole graph and gathers ALL rows on its own H/P-column slice:
     rows x all columns --all_to_all--> all rows x my columns --Phi--> --all_to_all--> rows x all columns
 The second all-to-all delivers one [n_local, H/P] block per peer; the tcgen05 stage kernel reads
 that blocked layout directly (``ndcn_solve_opts_t::z_block_cols``), so nothing is interleaved.
+``FeaturePushPartition`` combines the two ideas: the exchange volume of the feature-sharded gather with the
+push mechanism of ``PushPartition`` -- the producers of a gather source scatter every new row, column slice by
+column slice, into IPC-mapped slice buffers of all ranks, the slice gather stores z = Phi x straight into the
+blocked Z of the rank that owns each row, and two device barriers per RHS replace the two NCCL all-to-alls.
 ``exchange_volumes`` reports the bytes either scheme moves (``bench.py --exchange auto`` picks by it).
 
 ``PushPartition`` is the third scheme and the only one without a collective call on the path: the
@@ -411,6 +415,11 @@ class PushPartition:
                 cfg.delta_bytes[r] = (self.mapped[r] + self.PAD_BYTES - own_ws) + rows * self.H * 4
         return cfg
 
+    def configure(self, handle) -> None:
+        """Attach the peers to a freshly created solver handle (called by ``solver.odeint_fused``)."""
+        cfg = self.peer_config()
+        _ffi.check(_ffi.lib().ndcn_solver_set_peers(handle, C.byref(cfg)), "ndcn_solver_set_peers")
+
     def describe(self) -> dict:
         return {"scheme": "peer push (stage-kernel stores into IPC-mapped peer buffers + device barrier)",
                 "rows_local": self.n_local, "halo_rows": self.n_halo, "nnz_local": int(len(self.block.col)),
@@ -419,6 +428,128 @@ class PushPartition:
 
     def close(self, group=None) -> None:
         """Unmap the peers, then (after everybody has unmapped) free the own allocation."""
+        lib = _ffi.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                lib.ndcn_peer_close(p)
+            self._opened = []
+            if group is not False:
+                try:
+                    import torch.distributed as dist
+                    if dist.is_available() and dist.is_initialized():
+                        dist.barrier(group=group)
+                except Exception:
+                    pass
+            if self.base_ptr:
+                lib.ndcn_peer_free(self.base_ptr)
+                self.base_ptr = 0
+
+
+def _align(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+class FeaturePushPartition:
+    """Feature-sharded gather over peer memory (module docstring; ``ndcn_solver_set_feature_peers``).
+
+    Rank p owns rows ``[row0, row1)`` of the state (GEMM, solver algebra) and the column slice
+    ``[p Hc, (p+1) Hc)``, ``Hc = H / world``, of EVERY node (gather).  Per rank one IPC allocation holds the
+    signal pad, the slice buffer ``[N, Hc]`` and the blocked ``Z [world][n_local][Hc]``; the solver workspace
+    is private.  Same interface towards ``solver.odeint_fused(..., peers=part)`` as ``PushPartition``.
+    """
+
+    PAD_BYTES = 4096
+
+    def __init__(self, phi, world: int, rank: int, device: torch.device, H: int, method: str = "dopri5"):
+        n = phi.shape[0]
+        if world > 8 or H not in (128, 256) or H % world != 0 or (H // world) < 32 or ((H // world) & (H // world - 1)):
+            raise ValueError("feature-sharded push needs H in {128, 256} and H / world a power of two >= 32 "
+                             "(H=%d, world=%d)" % (H, world))
+        self.world, self.rank, self.device = int(world), int(rank), device
+        self.H, self.Hc, self.n, self.method = int(H), int(H // world), int(n), method
+        self.bounds = row_blocks(n, world)
+        self.row0, self.row1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.n_local, self.n_halo = self.row1 - self.row0, 0
+        self.full_graph = CsrGraph.from_scipy(phi.tocsr(), device)
+        # the solver works on a handle with the local rows and no entries: it never gathers itself
+        self.graph = CsrGraph(torch.zeros(self.n_local + 1, dtype=torch.int32, device=device),
+                              torch.zeros(0, dtype=torch.int32, device=device),
+                              torch.zeros(0, dtype=torch.float32, device=device), self.n_local, self.n_local)
+        lib = _ffi.lib()
+        self.xcs_bytes = _align(self.n * self.Hc * 4, 256)            # same on every rank: Z sits at the same offset
+        self.z_bytes = _align(self.n_local * self.H * 4, 256)
+        with torch.cuda.device(device):
+            self.workspace_bytes = int(lib.ndcn_solver_workspace_bytes(self.n_local, self.n_local, self.H,
+                                                                        _ffi.METHODS[method]))
+            self._ws = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=device)
+            ptr = C.c_void_p()
+            self._handle = C.create_string_buffer(64)
+            _ffi.check(lib.ndcn_peer_alloc(self.PAD_BYTES + self.xcs_bytes + self.z_bytes, C.byref(ptr), self._handle),
+                       "ndcn_peer_alloc")
+        self.base_ptr = int(ptr.value)
+        self.mapped: List[int] = []
+        self._opened: List[int] = []
+        self.n_solves = 0
+
+    @classmethod
+    def build(cls, phi, world: int, rank: int, device: torch.device, H: int, method: str = "dopri5",
+              group=None) -> "FeaturePushPartition":
+        import torch.distributed as dist
+
+        self = cls(phi, world, rank, device, H, method)
+        handles: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(handles, bytes(self._handle.raw), group=group)
+        lib = _ffi.lib()
+        with torch.cuda.device(device):
+            for r in range(world):
+                if r == rank:
+                    self.mapped.append(self.base_ptr)
+                    continue
+                p = C.c_void_p()
+                _ffi.check(lib.ndcn_peer_open(handles[r], C.byref(p)), "ndcn_peer_open")
+                self.mapped.append(int(p.value))
+                self._opened.append(int(p.value))
+        dist.barrier(group=group)
+        return self
+
+    @classmethod
+    def build_in_process(cls, phi, world: int, devices, H: int, method: str = "dopri5") -> List["FeaturePushPartition"]:
+        parts = [cls(phi, world, r, torch.device(devices[r]), H, method) for r in range(world)]
+        lib = _ffi.lib()
+        for a in parts:
+            a.mapped = [b.base_ptr for b in parts]
+            with torch.cuda.device(a.device):
+                for b in parts:
+                    if b.device != a.device:
+                        _ffi.check(lib.ndcn_peer_enable_access(b.device.index), "ndcn_peer_enable_access")
+        return parts
+
+    @property
+    def workspace_ptr(self) -> int:
+        return int(self._ws.data_ptr())
+
+    def configure(self, handle) -> None:
+        assert len(self.mapped) == self.world, "peers not mapped yet"
+        cfg = _ffi.FeaturePeerConfig()
+        cfg.rank, cfg.world = self.rank, self.world
+        for r in range(self.world):
+            cfg.pad[r] = self.mapped[r]
+            cfg.xcs[r] = self.mapped[r] + self.PAD_BYTES
+            cfg.z[r] = self.mapped[r] + self.PAD_BYTES + self.xcs_bytes
+        for r in range(9):
+            cfg.row_bounds[r] = int(self.bounds[min(r, self.world)])
+        _ffi.check(_ffi.lib().ndcn_solver_set_feature_peers(handle, self.full_graph.handle, C.byref(cfg)),
+                   "ndcn_solver_set_feature_peers")
+
+    def describe(self) -> dict:
+        per_rank = 2 * (self.world - 1) * self.n_local * self.Hc * 4
+        return {"scheme": "feature-sharded peer push (slice scatter in the stage epilogue, z scatter in the slice "
+                          "gather, 2 device barriers per RHS)",
+                "rows_local": self.n_local, "columns_local": self.Hc, "push_bytes_per_rhs": per_rank,
+                "solves": self.n_solves}
+
+    def close(self, group=None) -> None:
         lib = _ffi.lib()
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)

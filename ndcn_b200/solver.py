@@ -153,8 +153,8 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
     ``decoder=(W_d, b_d)``: apply ``Linear(H -> C)`` (NDCN.output_layer) to every returned state inside
     the solve; the result is ``[len(t), n_rows, C]`` and the ``[len(t), n_rows, H]`` slab is never written.
     ``exchange`` / ``z_block_cols``: multi-GPU hooks of ``ndcn_b200.partition`` (halo exchange of a
-    1-D row partition, or the feature-sharded gather).  ``peers``: a ``partition.PushPartition`` -- the
-    peer-push scheme (no hook: the solve runs in the partition's IPC-shared workspace and the library's
+    1-D row partition, or the feature-sharded gather).  ``peers``: a ``partition.PushPartition`` or
+    ``partition.FeaturePushPartition`` -- the peer-push schemes (no hook: the solve runs in the partition's IPC-shared workspace and the library's
     kernels store new gather-source rows straight into the other ranks' buffers); ``graph`` must be
     ``peers.graph`` and every rank must make the same calls in the same order.
     """
@@ -237,8 +237,7 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
             _ffi.check(lib.ndcn_solver_create(graph.handle, C.byref(desc), method_id, ws_ptr, ws_bytes,
                                               C.byref(handle)), "ndcn_solver_create")
             if peers is not None:
-                cfg = peers.peer_config()
-                _ffi.check(lib.ndcn_solver_set_peers(handle, C.byref(cfg)), "ndcn_solver_set_peers")
+                peers.configure(handle)
             if len(_SOLVERS) >= 8:
                 _, (old, _g) = _SOLVERS.popitem()
                 lib.ndcn_solver_destroy(old)

@@ -101,6 +101,39 @@ def case_umma(world, method):
         close(parts)
 
 
+def case_feature_push(world, H, method, n):
+    """Feature-sharded peer push: slice scatter from the stage epilogues / pre-stage algebra / y0 copy, slice
+    gather with z scattered to the row owners, blocked-Z tcgen05 stage kernel; ragged last block."""
+    import ndcn_b200 as nb
+    from ndcn_b200 import partition
+
+    phi = _operator(n, seed=world + H)
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(H, H)
+    W, b = (lin.weight.detach() * 0.5).to(dev), lin.bias.detach().to(dev)
+    x0 = torch.randn(n, H)
+    if method == "dopri5":
+        t = torch.tensor([0.0, 0.3, 0.55, 1.0], dtype=torch.float64)
+        kw = dict(method="dopri5", rtol=1e-2, atol=1e-3)
+    else:
+        t = torch.linspace(0, 1, 5, dtype=torch.float64)
+        kw = dict(method=method)
+    g = nb.CsrGraph.from_scipy(phi, dev)
+    ref = nb.odeint_fused(g, nb.RhsSpec.ndcn(H, W, b), x0.to(dev), t, **kw).cpu()
+    parts = partition.FeaturePushPartition.build_in_process(phi, world, [dev] * world, H, method)
+    try:
+        for _ in range(2):
+            res, infos = solve_ranks(parts, lambda: nb.RhsSpec.ndcn(H, W, b), x0, t, **kw)
+            got = torch.cat(res, dim=1)
+            torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+            assert torch.equal(got[0], x0)
+        terminal = solve_ranks(parts, lambda: nb.RhsSpec.ndcn(H, W, b), x0, t, terminal_only=True, **kw)[0]
+        torch.testing.assert_close(torch.cat(terminal, dim=0), ref[-1], rtol=1e-4, atol=1e-5)
+    finally:
+        close(parts)
+
+
 def case_small_width():
     """H=20 (the dynamics scripts' default): FP32-FMA stage kernels and k_epi_only push; adaptive dopri5
     must take the reference's step sequence on both ranks (the all-reduced error norm feeds both
@@ -162,6 +195,11 @@ CASES = [
     ("heat euler x3 ragged", lambda: case_heat(3, "euler", 5000)),
     ("heat rk4 x4", lambda: case_heat(4, "rk4", 5001)),
     ("heat midpoint x2", lambda: case_heat(2, "midpoint", 4999)),
+    ("feature push dopri5 x2 H=256", lambda: case_feature_push(2, 256, "dopri5", 9001)),
+    ("feature push dopri5 x4 H=128", lambda: case_feature_push(4, 128, "dopri5", 5003)),
+    ("feature push rk4 x8 H=256", lambda: case_feature_push(8, 256, "rk4", 4099)),
+    ("feature push euler x4 H=256", lambda: case_feature_push(4, 256, "euler", 3000)),
+    ("feature push midpoint x2 H=128", lambda: case_feature_push(2, 128, "midpoint", 2500)),
 ]
 
 
