@@ -238,8 +238,9 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
                                               C.byref(handle)), "ndcn_solver_create")
             if peers is not None:
                 peers.configure(handle)
-            if len(_SOLVERS) >= 8:
-                _, (old, _g) = _SOLVERS.popitem()
+            if len(_SOLVERS) >= 16:
+                oldest = next(iter(_SOLVERS))  # FIFO: never the handle another in-flight rank just created
+                old, _g = _SOLVERS.pop(oldest)
                 lib.ndcn_solver_destroy(old)
             if spec.callback is None:
                 _SOLVERS[key] = (handle, graph)
