@@ -41,10 +41,8 @@ T_TOTAL, STEPS_TOTAL = 5.0, 100  # north star: T=5, 100 dopri5 steps  ->  dt = 0
 DT = T_TOTAL / STEPS_TOTAL
 
 
-# measured on the 1M-node power-law graph (profiles/README.md): push 12.8 / 11.1 ms per step at 2 / 4 GPUs against
-# 18.7 (halo) / 12.3 (feature); at 8 GPUs every rank would receive 875 MB per RHS over NVLink (>= 1.2 ms), the
-# feature-sharded gather moves 224 MB and measured 7.2 ms per step
-PUSH_MAX_WORLD = 4
+PUSH_MAX_WORLD = 4    # whole-row peer push: beyond this every rank would receive > 0.8 GB per RHS over NVLink
+FPUSH_MIN_WORLD = 4   # feature-sharded peer push takes over here (pick_exchange has the measured table)
 PUSH_IN_AUTO = True  # `--exchange auto` may pick the peer-push scheme
 
 
@@ -262,22 +260,28 @@ def workload_config(args, n, nnz):
 # ----------------------------------------------------------------------------------------------
 # our arm
 def pick_exchange(vols: dict, world: int, H: int, allow_push: bool = True) -> str:
-    """`--exchange auto`.  Bytes per RHS and rank: halo and push move about the same on a graph without
-    locality, but push overlaps the transfer with the stage kernel and needs no pack pass, so it wins
-    wherever the halo exchange would be chosen on such a graph; the feature-sharded gather moves
-    2 (P-1)/P^2 of the state and takes over once that is far below the push volume (measured cross-over
-    on the 1M-node power-law graph: see profiles/README.md).  A graph WITH locality (halo much smaller
-    than the remote rows) keeps the NCCL halo exchange."""
+    """`--exchange auto`, from the measurements on the 1M-node power-law graph (ms per step, profiles/README.md):
+
+        GPUs   halo (NCCL)   feature (NCCL)   push    fpush
+          2       18.7           25.0         12.5    13.8
+          4       17.8           12.3         11.1     8.9
+          8       14.8            7.2           -      6.0
+
+    A graph WITH locality (halo far smaller than the remote rows, e.g. a grid) keeps the NCCL halo exchange: it
+    moves kilobytes where every other scheme moves the whole state.  Otherwise the peer-memory schemes win: whole
+    rows pushed from the stage kernels at 2 GPUs (same bytes as the halo exchange, but overlapped and without pack
+    pass), column slices from 4 GPUs on (2 (P-1)/P^2 of the state per RHS instead of (P-1)/P).  `allow_push` =
+    False (CUDA IPC unavailable) falls back to the NCCL schemes by volume."""
     feature_ok = vols.get("feature") is not None and H in (128, 256)
+    fpush_ok = feature_ok and (H // world) >= 32 and ((H // world) & (H // world - 1)) == 0 and world <= 8
     halo, push = vols["halo"], vols["push"]
     if halo < 0.5 * push:
-        if feature_ok and vols["feature"] < halo:
-            return "feature"
-        return "halo"
-    if feature_ok and world >= PUSH_MAX_WORLD + 1 and vols["feature"] < push:
-        return "feature"
+        return "feature" if (feature_ok and vols["feature"] < halo) else "halo"
     if allow_push and PUSH_IN_AUTO and world <= 8:
-        return "push"
+        if world >= FPUSH_MIN_WORLD and fpush_ok:
+            return "fpush"
+        if world <= PUSH_MAX_WORLD or not feature_ok:
+            return "push"
     if feature_ok and vols["feature"] < halo:
         return "feature"
     return "halo"

@@ -20,7 +20,9 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (n, H, method) in [(8192 * world + 5, 256, "dopri5"), (8192 * world + 5, 128, "rk4"), (3001, 20, "dopri5")]:
+    cases = [("push", 8192 * world + 5, 256, "dopri5"), ("push", 8192 * world + 5, 128, "rk4"), ("push", 3001, 20, "dopri5"),
+             ("fpush", 9001, 256, "dopri5"), ("fpush", 5003, 128, "rk4")]
+    for (scheme, n, H, method) in cases:
         phi = wl.graph_operator(wl.power_law_adjacency(n, 5, seed=1), "norm_lap")
         torch.manual_seed(0)
         lin = torch.nn.Linear(H, H)
@@ -32,7 +34,10 @@ def main():
         else:
             t = torch.linspace(0, 1, 6, dtype=torch.float64)
             kw = dict(method="rk4")
-        part = partition.PushPartition.build(phi, world, rank, dev, H, method)
+        if scheme == "fpush":  # feature-sharded peer push: column slices instead of whole rows
+            part = partition.FeaturePushPartition.build(phi, world, rank, dev, H, method)
+        else:
+            part = partition.PushPartition.build(phi, world, rank, dev, H, method)
         spec = nb.RhsSpec.ndcn(H, W, b)
         for rep in range(2):
             mine = nb.odeint_fused(part.graph, spec, x0[part.row0:part.row1].to(dev), t, peers=part, **kw)
@@ -49,8 +54,8 @@ def main():
             err = float((got - ref).abs().max())
             close = torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
             same = (info.nfe, info.n_accepted, info.n_rejected) == (ref_info.nfe, ref_info.n_accepted, ref_info.n_rejected)
-            print("push n=%d H=%d %s: max|diff|=%.3g close=%s counters %s vs %s" %
-                  (n, H, method, err, close, (info.nfe, info.n_accepted, info.n_rejected),
+            print("%s n=%d H=%d %s: max|diff|=%.3g close=%s counters %s vs %s" %
+                  (scheme, n, H, method, err, close, (info.nfe, info.n_accepted, info.n_rejected),
                    (ref_info.nfe, ref_info.n_accepted, ref_info.n_rejected)), flush=True)
             ok = ok and close and same
         dist.barrier()
