@@ -1,12 +1,15 @@
-"""GPU: the peer-push multi-GPU scheme (partition.PushPartition, ndcn_solver_set_peers).
+"""GPU: the peer-memory multi-GPU schemes -- whole-row peer push (partition.PushPartition,
+ndcn_solver_set_peers) and feature-sharded peer push (partition.FeaturePushPartition,
+ndcn_solver_set_feature_peers).
 
-The kernels that produce a gather source also store every new row into the other ranks' buffers and a
-device barrier kernel orders those stores before the next gather.
-  * test_push_ranks_in_one_process: two to four "ranks" run as threads of ONE process on ONE GPU
+The kernels that produce a gather source also store every new row (or column slice) into the other ranks'
+buffers and a device barrier kernel orders those stores before the next gather.
+  * test_push_ranks_in_one_process: two to eight "ranks" run as threads of ONE process on ONE GPU
     (tests/push_inproc_worker.py) -- the device addresses of the other ranks' workspaces are valid as
     they are, no IPC needed -- so the 1-GPU box exercises the whole path: full-halo graphs, the pushes
     from the tcgen05 stage kernels / the FP32-FMA kernels / the ground-truth dynamics kernels / the
-    pre-stage algebra, the barrier and its 2-double all-reduce.  Checked against the same solve on the
+    pre-stage algebra, the slice scatter / z-owner scatter of the feature-sharded variant, the barrier and
+    its 2-double all-reduce.  Checked against the same solve on the
     unpartitioned graph (itself parity-tested against the oracle) and, for one case, the CPU oracle.
   * test_push_two_gpus_torchrun: the real configuration, one process per GPU over CUDA IPC / NVLink
     (tests/push_worker.py); needs >= 2 GPUs.

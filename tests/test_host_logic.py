@@ -86,3 +86,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_bench_exchange_rule():
+    """bench.py --exchange auto: the measured table in pick_exchange (no GPU needed)."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    no_locality = {2: {"halo": 511e6, "push": 512e6, "feature": 512e6},
+                   4: {"halo": 760e6, "push": 768e6, "feature": 384e6},
+                   8: {"halo": 856e6, "push": 896e6, "feature": 224e6}}
+    assert [bench.pick_exchange(no_locality[p], p, 256) for p in (2, 4, 8)] == ["push", "fpush", "fpush"]
+    # CUDA IPC unavailable: NCCL schemes by volume
+    assert [bench.pick_exchange(no_locality[p], p, 256, allow_push=False) for p in (2, 4, 8)] == ["halo", "feature", "feature"]
+    # a grid: the halo is one line of nodes per neighbour
+    assert bench.pick_exchange({"halo": 2e6, "push": 768e6, "feature": 384e6}, 4, 256) == "halo"
+    # widths without a tcgen05 path have no slice schemes
+    assert bench.pick_exchange({"halo": 190e6, "push": 192e6, "feature": None}, 4, 64) == "push"
+    # H / world below 32 columns: no feature-sharded push
+    assert bench.pick_exchange({"halo": 428e6, "push": 448e6, "feature": None}, 8, 128) in ("push", "halo")
