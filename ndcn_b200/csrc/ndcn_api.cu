@@ -1455,6 +1455,14 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   } else {
     rc = run_fixed_grid(d, y0, t_host, n_t, out);
   }
+  if (d.push() && rc == 0) {
+    // a barrier that timed out has flagged it in this rank's signal pad (the fixed-grid drivers have no
+    // controller block that could carry the status)
+    int timed_out = 0;
+    cudaStreamSynchronize(st);
+    if (cudaMemcpy(&timed_out, &sv->peers.self->timed_out, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && timed_out)
+      rc = NDCN_E_PEER_TIMEOUT;
+  }
   if (d.timing) {
     cudaStreamSynchronize(st);
     d.t_collect(sv->method == NDCN_DOPRI5 ? (int64_t)sv->ctrl_host->n_attempt : (int64_t)1 << 60, stats);
