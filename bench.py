@@ -341,8 +341,10 @@ def main_ours(args):
                     part = partition.FeaturePushPartition.build(phi, world, rank, dev, H, meth)
                 else:
                     # rows per rank balanced by cost: 0.16 ns per gathered entry; per row the larger of the stage
-                    # kernel's own time (2.0 ns) and the NVLink push of (P-1) KB at ~750 GB/s
-                    row_ns = max(2.0, 1.37 * (world - 1) * H / 256.0)
+                    # kernel's own time and the NVLink push of (P-1) KB at ~750 GB/s.  2.9 ns per row = the fit to
+                    # the per-rank class times of the 2-GPU run with the first guess of 2.0 (rank 0 busy 11.3 ms with
+                    # 401k rows / 6.74M entries, rank 1 12.2 ms with 599k / 4.26M: 0.134 ns per entry, 2.44 ns per row)
+                    row_ns = max(2.9, 1.37 * (world - 1) * H / 256.0)
                     bounds = None if args.even_rows else partition.cost_balanced_blocks(phi, world, row_ns / 0.16)
                     part = partition.PushPartition.build(phi, world, rank, dev, H, meth, bounds=bounds)
             except Exception as exc:  # pragma: no cover - depends on the box
