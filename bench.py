@@ -13,9 +13,12 @@ memory and the result returned to the host (H2D + D2H inside the timed region).
     python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]      the reference's CPU path (oracle port)
 
-N > 1: launched by torch.distributed.run, one rank per GPU; the graph is partitioned 1-D by
-node rows, halo rows are exchanged with NCCL before every RHS evaluation ("strong" scaling:
-the 1M-node problem is fixed).  Prints ONE JSON line on rank 0.
+N > 1: launched by torch.distributed.run, one rank per GPU; the state is partitioned 1-D by
+node rows ("strong" scaling: the 1M-node problem is fixed) and the neighbour rows every RHS
+evaluation needs travel by one of four schemes (``--exchange``, default ``auto`` = pick_exchange():
+peer push at 2 GPUs, feature-sharded peer push from 4 GPUs on -- the library's kernels store into
+the other ranks' IPC-mapped memory, no NCCL call on the path -- and the NCCL halo exchange for graphs
+with locality).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -324,9 +327,9 @@ def main_ours(args):
         part = None
     else:
         from ndcn_b200 import partition
-        # three exchange schemes (ndcn_b200/partition.py): NCCL halo exchange of a 1-D row partition, the
-        # feature-sharded gather (2 NCCL all-to-alls), or peer push (stage kernels store into IPC-mapped
-        # peer buffers); `auto` = pick_exchange()
+        # four exchange schemes (ndcn_b200/partition.py): NCCL halo exchange of a 1-D row partition, the
+        # feature-sharded gather (2 NCCL all-to-alls), and the two peer-memory schemes (the library's kernels store
+        # whole rows / column slices into IPC-mapped peer buffers); `auto` = pick_exchange()
         vols = partition.exchange_volumes(phi, world, H)
         scheme = args.exchange
         if scheme == "auto":
