@@ -1546,6 +1546,12 @@ extern "C" int ndcn_solver_set_feature_peers(ndcn_solver_t* sv, const ndcn_graph
   }
   for (int r = 0; r <= 8; ++r) t.bounds[r] = (int)cfg->row_bounds[r <= P ? r : P];
   t.world = P;
+  t.n_total = (int)cfg->row_bounds[P];
+  t.nl_uniform = (int)(cfg->row_bounds[1] - cfg->row_bounds[0]);
+  for (int r = 0; r < P; ++r) {
+    const int64_t want = std::min<int64_t>((int64_t)r * t.nl_uniform, t.n_total);
+    if (cfg->row_bounds[r] != want) t.nl_uniform = 0;  // ragged blocks: owner by table walk
+  }
   if (!sv->feat_dev) CU_TRY(cudaMalloc((void**)&sv->feat_dev, sizeof(FeatTable)));
   CU_TRY(cudaMemcpy(sv->feat_dev, &t, sizeof(t), cudaMemcpyHostToDevice));
   std::memset(&sv->peers, 0, sizeof(sv->peers));

@@ -66,6 +66,8 @@ struct FeatTable {
   float* z[8];    // rank q's Z [world][n_local_q][Hc]        (IPC-mapped)
   int bounds[9];  // row-block boundaries of the ranks (entries past `world` repeat the last one)
   int world;
+  int nl_uniform; // > 0: every block but the last has exactly this many rows (owner = row / nl_uniform)
+  int n_total;    // all rows
 };
 enum FeatMode : int { FEAT_OFF = 0, FEAT_Y_SLICES = 1, FEAT_Z_OWNERS = 2 };
 
@@ -248,10 +250,19 @@ __device__ __noinline__ void store_z_owner(const FeatTable* __restrict__ f, int 
                                            float v0, float v1, float v2, float v3) {
   const int64_t row = off >> hc_log2;
   const int col = (int)(off & (((int64_t)1 << hc_log2) - 1));
-  int o = 0;
+  int o, lo, hi;
+  const int nl = f->nl_uniform;
+  if (nl > 0) {  // uniform blocks: no table walk, one dependent load (the owner's Z pointer) per store
+    o = (int)((uint32_t)row / (uint32_t)nl);
+    lo = o * nl;
+    hi = min(lo + nl, f->n_total);
+  } else {
+    o = 0;
 #pragma unroll
-  for (int j = 1; j < 8; ++j) o += (row >= f->bounds[j] && j < f->world) ? 1 : 0;  // bounds ascend: owner = # of cuts <= row
-  const int lo = f->bounds[o], hi = f->bounds[o + 1];
+    for (int j = 1; j < 8; ++j) o += (row >= f->bounds[j] && j < f->world) ? 1 : 0;  // bounds ascend: owner = # of cuts <= row
+    lo = f->bounds[o];
+    hi = f->bounds[o + 1];
+  }
   float* dst = f->z[o] + (((int64_t)rank * (hi - lo) + (row - lo)) << hc_log2) + col;
   if constexpr (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
   else if constexpr (VW == 2) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);

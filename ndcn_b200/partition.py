@@ -104,6 +104,16 @@ class LocalBlock:
         return int(len(self.halo_global))
 
 
+def uniform_blocks(n: int, world: int) -> np.ndarray:
+    """Block boundaries [world + 1] with ceil(n / world) rows in every block but the last: the owner of a row is
+    ``row // block`` (the feature-sharded push computes it per store instead of walking a table)."""
+    nl = -(-n // world)
+    b = np.minimum(np.arange(world + 1, dtype=np.int64) * nl, n)
+    if not bool((np.diff(b) > 0).all()):
+        return row_blocks(n, world)  # tiny graphs: fall back to sizes differing by one
+    return b
+
+
 def halo_row_offset(bounds: np.ndarray, src_rank: int, dst_rank: int) -> int:
     """Full-halo layout: the row of ``dst_rank``'s gather-source buffer at which ``src_rank``'s block
     starts.  A buffer is [own rows | all remote rows in global order], so the blocks of lower ranks
@@ -461,14 +471,16 @@ class FeaturePushPartition:
 
     PAD_BYTES = 4096
 
-    def __init__(self, phi, world: int, rank: int, device: torch.device, H: int, method: str = "dopri5"):
+    def __init__(self, phi, world: int, rank: int, device: torch.device, H: int, method: str = "dopri5",
+                 bounds: Optional[np.ndarray] = None):
         n = phi.shape[0]
         if world > 8 or H not in (128, 256) or H % world != 0 or (H // world) < 32 or ((H // world) & (H // world - 1)):
             raise ValueError("feature-sharded push needs H in {128, 256} and H / world a power of two >= 32 "
                              "(H=%d, world=%d)" % (H, world))
         self.world, self.rank, self.device = int(world), int(rank), device
         self.H, self.Hc, self.n, self.method = int(H), int(H // world), int(n), method
-        self.bounds = row_blocks(n, world)
+        self.bounds = uniform_blocks(n, world) if bounds is None else np.asarray(bounds, np.int64)
+        assert len(self.bounds) == world + 1 and self.bounds[0] == 0 and self.bounds[-1] == n
         self.row0, self.row1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
         self.n_local, self.n_halo = self.row1 - self.row0, 0
         self.full_graph = CsrGraph.from_scipy(phi.tocsr(), device)
@@ -514,8 +526,9 @@ class FeaturePushPartition:
         return self
 
     @classmethod
-    def build_in_process(cls, phi, world: int, devices, H: int, method: str = "dopri5") -> List["FeaturePushPartition"]:
-        parts = [cls(phi, world, r, torch.device(devices[r]), H, method) for r in range(world)]
+    def build_in_process(cls, phi, world: int, devices, H: int, method: str = "dopri5",
+                         bounds: Optional[np.ndarray] = None) -> List["FeaturePushPartition"]:
+        parts = [cls(phi, world, r, torch.device(devices[r]), H, method, bounds) for r in range(world)]
         lib = _ffi.lib()
         for a in parts:
             a.mapped = [b.base_ptr for b in parts]

@@ -101,7 +101,7 @@ def case_umma(world, method):
         close(parts)
 
 
-def case_feature_push(world, H, method, n):
+def case_feature_push(world, H, method, n, ragged=False):
     """Feature-sharded peer push: slice scatter from the stage epilogues / pre-stage algebra / y0 copy, slice
     gather with z scattered to the row owners, blocked-Z tcgen05 stage kernel; ragged last block."""
     import ndcn_b200 as nb
@@ -121,7 +121,9 @@ def case_feature_push(world, H, method, n):
         kw = dict(method=method)
     g = nb.CsrGraph.from_scipy(phi, dev)
     ref = nb.odeint_fused(g, nb.RhsSpec.ndcn(H, W, b), x0.to(dev), t, **kw).cpu()
-    parts = partition.FeaturePushPartition.build_in_process(phi, world, [dev] * world, H, method)
+    # default: uniform blocks (owner = row // block); ragged: sizes differing by one (owner by table walk)
+    bounds = partition.row_blocks(n, world) if ragged else None
+    parts = partition.FeaturePushPartition.build_in_process(phi, world, [dev] * world, H, method, bounds=bounds)
     try:
         for _ in range(2):
             res, infos = solve_ranks(parts, lambda: nb.RhsSpec.ndcn(H, W, b), x0, t, **kw)
@@ -200,6 +202,7 @@ CASES = [
     ("feature push rk4 x8 H=256", lambda: case_feature_push(8, 256, "rk4", 4099)),
     ("feature push euler x4 H=256", lambda: case_feature_push(4, 256, "euler", 3000)),
     ("feature push midpoint x2 H=128", lambda: case_feature_push(2, 128, "midpoint", 2500)),
+    ("feature push dopri5 x4 H=256 ragged blocks", lambda: case_feature_push(4, 256, "dopri5", 4099, ragged=True)),
 ]
 
 

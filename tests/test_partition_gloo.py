@@ -208,3 +208,14 @@ def test_cost_balanced_blocks(world):
                 buf[off:off + (bal[src + 1] - bal[src])] = x[bal[src]:bal[src + 1]]
         local = sp.csr_matrix((blk.val, blk.col, blk.rowptr), shape=(blk.n_local, n))
         assert np.allclose(local @ buf, ref[bal[r]:bal[r + 1]], rtol=1e-5, atol=1e-6)
+
+
+def test_uniform_blocks():
+    for n, world in [(1_000_000, 8), (4099, 8), (9001, 2), (5003, 4), (64, 8)]:
+        b = partition.uniform_blocks(n, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1 and (np.diff(b) > 0).all()
+        nl = int(b[1])
+        rows = np.arange(n)
+        assert np.array_equal(np.searchsorted(b, rows, side="right") - 1, np.minimum(rows // nl, world - 1))
+    # too few rows for ceil-sized blocks: falls back to sizes differing by one
+    assert np.array_equal(partition.uniform_blocks(9, 8), partition.row_blocks(9, 8))
