@@ -552,6 +552,16 @@ def main_ours(args):
             line["config"]["parallelism"] = "1-D node-row partition x%d, NCCL halo exchange before every RHS eval" % world
         line["partition"] = part.describe()
         line["partition"]["exchange_bytes_per_rhs_and_rank"] = vols
+        # per-rank device time by kernel class (ms per step, CUDA events of the timed solve): where the ranks differ
+        # -- `exchange` is the time inside the barrier kernels, i.e. mostly waiting for the slowest rank
+        try:
+            mine = {k: round(float(v) / K, 4) for k, v in roofline["class_ms"].items()}
+            mine["rows"] = int(graph.n_rows)
+            by_rank = [None] * world
+            dist.all_gather_object(by_rank, mine)
+            line["partition"]["class_ms_per_step_by_rank"] = by_rank
+        except Exception as exc:  # diagnostics only: never cost the bench line
+            line["partition"]["class_ms_per_step_by_rank"] = "unavailable: %s" % (exc,)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del x0, out_buf
