@@ -1,41 +1,43 @@
-"""1-D node-row partition of the operator Phi and the halo exchange for multi-GPU solves.
+"""Multi-GPU: 1-D node-row partition of the state and the four ways the neighbour rows travel.
 
-The reference is single-device; this is the sharding BASELINE.json's
-north star prescribes: rank p owns the contiguous row block [row0, row1) of Phi and of the
-state; its local CSR has the columns remapped to ``[local rows | halo rows]`` where the halo is
-the sorted set of remote rows its block references, grouped by owner.  Before every RHS
-evaluation the solver calls ``exchange(what=0, buf)``: boundary rows are packed with the
-library's gather kernel (``ndcn_pack_rows_f32``) and moved with ONE ``all_to_all_single`` over
-NCCL (NVLink 5 / NVSwitch) straight into the halo region of the gather source.  The dopri5
-error norm needs one 2-double all-reduce per step (``what=1``).
+The reference is single-device.  Here rank p owns the contiguous row block
+[row0, row1) of the state; the GEMM, the Runge-Kutta algebra and the error norm are row-local, the gather
+Phi x is not.  Host logic (index building) is numpy and covered by gloo / numpy tests on the CPU.
 
-Host logic (index building) is numpy and is covered by world_size-2 gloo tests on the CPU; the
-exchange itself takes the communication backend of the default process group.
+NCCL schemes (exchange hook of ``ndcn_solve_opts_t``, ``solver.odeint_fused(..., exchange=part.exchange)``):
 
-``FeaturePartition`` is the second scheme, for graphs WITHOUT locality (power-law, ER): there the
-halo of a row block is nearly every remote row (0.64 GB per RHS and rank at
-N=1M, P=8), while transposing the state costs 2 (P-1)/P * 4NH/P bytes per rank (0.22 GB).  The
-state stays row-sharded for the GEMM and the solver algebra; for the gather every rank holds the
-whole graph and gathers ALL rows on its own H/P-column slice:
+``RowPartition`` -- the north star's halo exchange.  The local CSR has its columns remapped to
+``[local rows | halo rows]``, the halo being the sorted set of remote rows the block references.  Before every
+RHS evaluation (``what=0``) boundary rows are packed by ``ndcn_pack_rows_f32`` and moved with ONE
+``all_to_all_single`` into the halo region of the gather source; the dopri5 error norm is one 2-double
+all-reduce per step (``what=1``).  Right for graphs WITH locality (a grid block needs one line of nodes).
+
+``FeaturePartition`` -- for graphs WITHOUT locality (power-law, ER) the halo of a row block is nearly every
+remote row (0.86 GB per RHS and rank at N=1M, P=8), while transposing the state costs 2 (P-1)/P * 4NH/P bytes
+(0.22 GB).  Every rank holds the whole graph and gathers ALL rows on its own H/P-column slice:
     rows x all columns --all_to_all--> all rows x my columns --Phi--> --all_to_all--> rows x all columns
-The second all-to-all delivers one [n_local, H/P] block per peer; the tcgen05 stage kernel reads
-that blocked layout directly (``ndcn_solve_opts_t::z_block_cols``), so nothing is interleaved.
-``FeaturePushPartition`` combines the two ideas: the exchange volume of the feature-sharded gather with the
-push mechanism of ``PushPartition`` -- the producers of a gather source scatter every new row, column slice by
-column slice, into IPC-mapped slice buffers of all ranks, the slice gather stores z = Phi x straight into the
-blocked Z of the rank that owns each row, and two device barriers per RHS replace the two NCCL all-to-alls.
-``exchange_volumes`` reports the bytes either scheme moves (``bench.py --exchange auto`` picks by it).
+The second all-to-all delivers one [n_local, H/P] block per peer; the tcgen05 stage kernel reads that blocked
+layout directly (``ndcn_solve_opts_t::z_block_cols``, ``what=2``).
 
-``PushPartition`` is the third scheme and the only one without a collective call on the path: the
-local CSR takes a FULL halo (every remote row, ``n_cols`` = all nodes), every rank maps the other ranks'
-solver workspaces with CUDA IPC (NVLink peer memory), and the kernels that produce a gather source
-(tcgen05 stage kernels, pre-stage algebra) store each new row into their own buffer and into the halo
-region of every peer while they compute -- the all-gather of the north star, fused into the producing
-kernel's epilogue.  A one-block barrier kernel over IPC-shared signal pads (``k_peer_barrier``) orders
-those stores before the next gather and carries the dopri5 controller's 2-double all-reduce, so a solve
-issues no NCCL call, no Python hook and no per-step host synchronisation.  Volume per RHS and rank:
-(P-1) * n_local * H * 4 bytes out -- 512 MB at P=2 (what the halo exchange moves too, but overlapped with
-the stage kernel and without the pack pass), 896 MB at P=8 (there the feature-sharded scheme moves 224 MB).
+Peer-memory schemes (``solver.odeint_fused(..., peers=part)``): no hook, no NCCL call, no Python between
+kernels and no per-step host synchronisation.  Every rank maps the other ranks' buffers with CUDA IPC
+(NVLink), the library's own kernels store into them while they compute, and a one-block barrier kernel over
+IPC-shared signal pads (``k_peer_barrier``) orders those stores before the next gather and carries the dopri5
+controller's 2-double all-reduce:
+
+``PushPartition`` -- whole rows: the local CSR takes a FULL halo (every remote row, ``n_cols`` = all nodes) and
+the kernels that produce a gather source (tcgen05 stage kernels, pre-stage algebra) store each new row into
+their own buffer and into the halo region of every peer -- the all-gather, fused into the producer's epilogue.
+(P-1) * n_local * H * 4 bytes out per RHS and rank: what the halo exchange moves at P=2, but overlapped with
+the stage kernel and without the pack pass.  Row blocks may be cost-balanced (``cost_balanced_blocks``).
+
+``FeaturePushPartition`` -- column slices: the volume of the feature-sharded gather with the push mechanism.
+Producers scatter every new row, slice by slice, into the slice buffers of all ranks; the slice gather stores
+z = Phi x straight into the blocked Z of the rank that owns each row; two device barriers per RHS replace
+the two all-to-alls.
+
+``exchange_volumes`` reports the bytes each scheme moves (``bench.py --exchange auto`` decides with it; measured
+on the 1M-node power-law graph: peer push at 2 GPUs, feature-sharded push from 4 GPUs on).
 """
 from __future__ import annotations
 
