@@ -1493,11 +1493,11 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
 // ---------------------------------------------------------------------------------------
 extern "C" int ndcn_solver_set_peers(ndcn_solver_t* sv, const ndcn_peer_config_t* cfg) {
   if (!sv) return NDCN_E_ARG;
+  if (sv->feat_on) return NDCN_E_ARG;  // one scheme at a time (the feature-sharded push owns sv->peers)
   sv->n_push = 0;
   std::memset(&sv->peers, 0, sizeof(sv->peers));
   if (!cfg || cfg->world <= 1) return NDCN_OK;
   if (cfg->world > kMaxPeers + 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return NDCN_E_ARG;
-  if (sv->feat_on) return NDCN_E_ARG;                // one scheme at a time
   if (sv->n_cols <= sv->n_rows) return NDCN_E_ARG;  // needs halo rows to push into
   if (sv->rhs.kind == NDCN_RHS_CALLBACK) return NDCN_E_ARG;
   for (int r = 0; r < cfg->world; ++r)
