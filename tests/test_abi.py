@@ -52,6 +52,21 @@ def test_argument_validation_without_gpu():
     assert lib.ndcn_odeint_f32(None, None, None, 0, None, None, None, None) == _ffi.E_ARG
 
 
+def test_peer_api_argument_validation_without_gpu():
+    """multi-GPU peer-memory entry points reject null / malformed arguments before touching the device"""
+    lib = _ffi.lib()
+    assert lib.ndcn_solver_set_peers(None, None) == _ffi.E_ARG
+    assert lib.ndcn_solver_set_feature_peers(None, None, None) == _ffi.E_ARG
+    ptr = ctypes.c_void_p()
+    assert lib.ndcn_peer_alloc(0, ctypes.byref(ptr), ctypes.create_string_buffer(64)) == _ffi.E_ARG
+    assert lib.ndcn_peer_alloc(4096, None, ctypes.create_string_buffer(64)) == _ffi.E_ARG
+    assert lib.ndcn_peer_open(None, ctypes.byref(ptr)) == _ffi.E_ARG
+    assert lib.ndcn_peer_close(None) == _ffi.OK and lib.ndcn_peer_free(None) == _ffi.OK
+    # struct layouts the library reads: sizes must match the C side (8-byte aligned fields)
+    assert ctypes.sizeof(_ffi.PeerConfig) == 8 + 8 * 8 + 8 * 8
+    assert ctypes.sizeof(_ffi.FeaturePeerConfig) == 8 + 3 * 8 * 8 + 9 * 8
+
+
 def test_sass_has_bulk_copy_and_no_legacy_paths():
     """The W^T chunks move with cp.async.bulk (SASS UBLKCP); built for sm_100a only."""
     import shutil
