@@ -11,7 +11,11 @@ same solve through the public ``ndcn_b200.odeint(ODEFunc, y0, t)`` call with y0 
 memory and the result returned to the host (H2D + D2H inside the timed region).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]      the reference's CPU path (oracle port)
+    python bench.py --impl reference [--steps K] [--warmup W]      the reference's own CPU path: the unmodified
+                                                                   torchdiffeq.odeint(neural_dynamics.ODEFunc ...) from
+                                                                   baseline/_ref (oracle port when that copy is absent)
+    python bench.py --config {3,4,5}                               the other BASELINE.json configurations (presets)
+    python bench.py --rhs {heat,gene,mutual} --hidden 1 ...        the ground-truth right-hand sides at scale
 
 N > 1: launched by torch.distributed.run, one rank per GPU; the state is partitioned 1-D by
 node rows ("strong" scaling: the 1M-node problem is fixed) and the neighbour rows every RHS
@@ -69,15 +73,34 @@ def parse_args():
     ap.add_argument("--even-rows", action="store_true",
                     help="multi-GPU push: equal row counts per rank instead of cost-balanced row blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the comparison with the single-GPU solve")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds for the cpu_baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="CPU seconds for the cpu_baseline sample")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: CPU seconds for the whole run")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4, 5],
+                    help="BASELINE.json preset: 0 north star (1M power-law, dopri5; default), 3 power-law 100489 nodes "
+                         "RK4 (3/8 rule), 4 ER 1M dopri5, 5 power-law 4M dopri5; explicit flags override the preset")
+    ap.add_argument("--rhs", choices=["ndcn", "heat", "gene", "mutual"], default="ndcn",
+                    help="right-hand side: the NDCN ODEFunc (default) or a ground-truth dynamics (use --hidden 1)")
+    args = ap.parse_args()
+    preset = {0: {}, 3: dict(nodes=317 * 317, graph="power_law", method="rk4"),
+              4: dict(nodes=1_000_000, graph="er", method="dopri5"),
+              5: dict(nodes=4_000_000, graph="power_law", method="dopri5")}[args.config]
+    given = {a.split("=")[0].lstrip("-").replace("-", "_") for a in sys.argv[1:] if a.startswith("--")}
+    for k, v in preset.items():
+        if k not in given:
+            setattr(args, k, v)
+    return args
 
 
 # ----------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------
 def build_operator(args, n):
+    """Phi of the workload: the normalized Laplacian for the NDCN ODEFunc (the scripts' default operator,
+    heat_dynamics.py:160-161), -L = A - D for HeatDiffusion (heat_dynamics.py:116-117,190), the adjacency for
+    GeneDynamics / MutualDynamics (gene_dynamics.py:209)."""
     from ndcn_b200 import workloads as wl
 
     if args.graph == "power_law":
@@ -89,6 +112,13 @@ def build_operator(args, n):
         a = wl.grid_adjacency(side)
     if args.layout == "degree":
         a, _ = wl.reorder_by_degree(a)
+    kind = getattr(args, "rhs", "ndcn")
+    if kind == "heat":
+        m = (-wl.graph_operator(a, "lap")).tocsr()
+        m.sort_indices()
+        return m
+    if kind in ("gene", "mutual"):
+        return a.astype(np.float32).tocsr()
     return wl.graph_operator(a, "norm_lap")
 
 
@@ -99,16 +129,19 @@ def make_weights(H):
     return (lin.weight.detach() * 0.5).contiguous(), lin.bias.detach().contiguous()
 
 
-def make_state(n, H, pin):
+def make_state(n, H, pin, positive=False):
     g = torch.Generator().manual_seed(0)
     x = torch.empty((n, H), dtype=torch.float32, pin_memory=pin)
     x.normal_(generator=g)
+    if positive:  # the ground-truth dynamics live on non-negative states (x0 of the scripts: 0 .. 25)
+        x.abs_()
     return x
 
 
-def bytes_rhs(n, nnz, H):
-    """algorithmic bytes of one RHS evaluation."""
-    return 2 * 4 * n * H + 8 * nnz + 4 * (n + 1) + 4 * H * H + 4 * H
+def bytes_rhs(n, nnz, H, rhs="ndcn"):
+    """algorithmic bytes of one RHS evaluation (state in, k out, CSR once [, W, b])."""
+    base = 2 * 4 * n * H + 8 * nnz + 4 * (n + 1)
+    return base + (4 * H * H + 4 * H if rhs == "ndcn" else 0)
 
 
 RHS_PER_STEP = {"dopri5": 6, "rk4": 4, "euler": 1}
@@ -170,76 +203,156 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# the reference's CPU path (oracle port; bit-identical to the reference on the same torch build,
-# tests/test_oracle_pinning.py) on a bounded sample
+# the reference's own implementation of the path, on the host cores (cpu_baseline / --impl reference) or on
+# cuda:0 (gpu_baseline: cuSPARSE + cuBLAS + Python-issued elementwise kernels)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup, budget_s):
-    """Times `steps` forced-dt steps of the reference algorithm on the host cores, on a graph of the
-    same family whose size is chosen so that warmup+steps fit in ~budget_s seconds."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_modules():
+    """(neural_dynamics, torchdiffeq) of the UNMODIFIED reference copy in baseline/_ref, or None."""
+    if not os.path.isfile(os.path.join(REF_DIR, "neural_dynamics.py")):
+        return None
+    from oracle import ref_loader
+
+    ref_loader.REFERENCE_ROOT = REF_DIR
+    return ref_loader.import_reference()
+
+
+def _sample_operator(args, n):
     from ndcn_b200 import workloads as wl
+
+    a = wl.power_law_adjacency(n, 5, seed=0) if args.graph == "power_law" else \
+        (wl.erdos_renyi_adjacency(n, 10.0, seed=0) if args.graph == "er" else wl.grid_adjacency(int(round(n ** .5))))
+    return wl.to_reference_coo(wl.graph_operator(a, "norm_lap"))
+
+
+def reference_run(args, device, budget_s, n_fixed=None):
+    """The reference algorithm on `device` for the bench workload (NDCN ODEFunc, H, graph family), on a graph
+    whose size is the full one when the estimated run fits `budget_s` seconds, else the largest that does.
+
+    With baseline/_ref present this is the reference's own code: ``torchdiffeq.odeint(neural_dynamics.ODEFunc(H,
+    Phi_coo), x0, t, ...)`` under no_grad, Phi an uncoalesced fp32 COO tensor as ``utils.py:12-23`` builds it
+    (kind "reference"); otherwise the oracle port (kind "port").  The reference's dopri5 has no fixed-step mode, so
+    it runs adaptively with the NDCN tolerances (rtol .01 / atol .001, neural_dynamics.py:123-126) over T=5 and the
+    work is counted in step equivalents of 6 RHS evaluations (nfe / 6: the initial-step probe's 2 evaluations
+    count as a third of a step); rk4 / euler run exactly `steps` grid steps."""
     from oracle import ndcn_oracle as O
 
+    is_cpu = device.type == "cpu"
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    if is_cpu:
+        torch.set_num_threads(cores)
     H = args.hidden
     W, b = make_weights(H)
     per_step = RHS_PER_STEP[args.method]
+    mods = _reference_modules()
 
-    def setup(n):
-        a = wl.power_law_adjacency(n, 5, seed=0) if args.graph == "power_law" else \
-            (wl.erdos_renyi_adjacency(n, 10.0, seed=0) if args.graph == "er" else wl.grid_adjacency(int(round(n ** .5))))
-        phi = wl.to_reference_coo(wl.graph_operator(a, "norm_lap"))
-        return phi, make_state(phi.shape[0], H, False)
+    def sync():
+        if not is_cpu:
+            torch.cuda.synchronize(device)
 
-    # calibrate on a small graph: seconds per (node * RHS evaluation)
+    def make_func(phi):
+        if mods is not None:
+            nd, _ = mods
+            f = nd.ODEFunc(H, phi.to(device))
+            with torch.no_grad():
+                f.wt.weight.copy_(W)
+                f.wt.bias.copy_(b)
+            return f.to(device).eval()
+        Wd, bd, pd = W.to(device), b.to(device), phi.to(device)
+        return lambda tt, xx: O.rhs_ndcn(pd, Wd, bd, xx)
+
+    # calibrate: seconds per (node x RHS evaluation) on a small graph of the same family
     n_cal = min(args.nodes, 32768)
-    phi, x = setup(n_cal)
+    phi = _sample_operator(args, n_cal)
+    f = make_func(phi)
+    x = make_state(phi.shape[0], H, False).to(device)
     with torch.no_grad():
-        O.rhs_ndcn(phi, W, b, x)
+        f(None, x)
+        sync()
         t0 = time.perf_counter()
         for _ in range(2):
-            O.rhs_ndcn(phi, W, b, x)
+            f(None, x)
+        sync()
         per_node_eval = (time.perf_counter() - t0) / 2 / n_cal
-    # a step costs ~ per_step RHS + ~as much again in solver algebra (SURVEY.md section 2.3)
-    est_per_node_step = per_node_eval * per_step * 2.0
-    n = int(budget_s / max(est_per_node_step * (steps + warmup), 1e-12))
+    # a step costs ~ per_step RHS + ~as much again in solver algebra (SURVEY.md section 2.3); dopri5 adaptive over
+    # T=5 takes ~3.3 step equivalents + a 1.3-step warm-up solve, fixed grids 3 steps + 1 warm-up
+    steps_est = 4.7 if args.method == "dopri5" else 4.0
+    n = n_fixed or int(budget_s / max(per_node_eval * per_step * 2.0 * steps_est, 1e-12))
     n = max(4096, min(args.nodes, n))
     if n != n_cal:
-        phi, x = setup(n)
+        del f, x, phi
+        phi = _sample_operator(args, n)
+        f = make_func(phi)
+        x = make_state(phi.shape[0], H, False).to(device)
     n = phi.shape[0]
 
-    def run(k):
-        t = torch.tensor([0.0, DT * (k - 0.5)], dtype=torch.float64)  # inside the k-th step: exactly k steps
-        func = lambda tt, xx: O.rhs_ndcn(phi, W, b, xx)  # noqa: E731
-        with torch.no_grad():
-            if args.method == "dopri5":
-                return O.odeint(func, x, t, method="dopri5", forced_dt=DT)
-            return O.odeint(func, x, torch.linspace(0, DT * k, k + 1), method=args.method)
+    class Counted(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner, self.nfe = inner, 0
 
-    if warmup > 0:
-        run(warmup)
-    t0 = time.perf_counter()
-    run(steps)
-    dt = time.perf_counter() - t0
-    value = n * H * steps / dt
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d-node %s graph (same generator), H=%d, %d forced-dt %s steps after %d warm-up, "
-                      "torch %s CPU, reference algorithm via oracle port (COO sparse.mm + Linear + per-op solver algebra)"
-                      % (n, args.graph, H, steps, args.method, warmup, torch.__version__),
-            "seconds": dt, "ms_per_step": 1e3 * dt / steps, "nodes": n}
+        def forward(self, tt, xx):
+            self.nfe += 1
+            return self.inner(tt, xx)
+
+    cf = Counted(f)
+    odeint = mods[1].odeint if mods is not None else None
+
+    def run(t, method, **kw):
+        with torch.no_grad():
+            if odeint is not None:
+                return odeint(cf, x, t.to(device), method=method, **kw)
+            return O.odeint(cf, x, t, method=method, **kw)
+
+    if args.method == "dopri5":
+        run(torch.tensor([0.0, 0.05]), "dopri5", rtol=.01, atol=.001)  # warm-up: init probe + first attempts
+        sync()
+        cf.nfe = 0
+        t0 = time.perf_counter()
+        run(torch.tensor([0.0, T_TOTAL]), "dopri5", rtol=.01, atol=.001)
+        sync()
+        dt = time.perf_counter() - t0
+        steps_eq = cf.nfe / 6.0
+        how = "adaptive dopri5 rtol=.01 atol=.001 over T=%g: nfe=%d = %.2f step equivalents of 6 RHS" % (T_TOTAL, cf.nfe, steps_eq)
+    else:
+        run(torch.linspace(0, DT, 2), args.method)
+        sync()
+        k = 3
+        t0 = time.perf_counter()
+        run(torch.linspace(0, DT * k, k + 1), args.method)
+        sync()
+        dt = time.perf_counter() - t0
+        steps_eq = float(k)
+        how = "%d %s grid steps of dt=%g after 1 warm-up step" % (k, args.method, DT)
+    value = n * H * steps_eq / dt
+    kind = "reference" if mods is not None else "port"
+    what = ("unmodified reference torchdiffeq.odeint(neural_dynamics.ODEFunc) from baseline/_ref" if mods is not None
+            else "oracle port of the reference algorithm (baseline/_ref absent)")
+    where = ("%d host threads" % cores) if is_cpu else ("cuda:%d (cuSPARSE/cuBLAS/ATen elementwise)" % (device.index or 0))
+    return {"value": value, "unit": UNIT, "cores": cores if is_cpu else 0, "kind": kind,
+            "sample": "%d-node %s graph (same generator as the workload), H=%d, Phi as uncoalesced fp32 COO; %s; %s; "
+                      "torch %s on %s" % (n, args.graph, H, how, what, torch.__version__, where),
+            "seconds": dt, "ms_per_step": 1e3 * dt / steps_eq, "nodes": n, "steps_eq": steps_eq}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    budget = 120.0
-    res = cpu_reference_run(args, args.steps, args.warmup, budget)
+    if args.rhs != "ndcn":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm covers the NDCN ODEFunc workload only"}))
+        return 0
+    res = reference_run(args, torch.device("cpu"), args.ref_budget_s)
+    cfg = workload_config(args, res["nodes"], None)
+    cfg["workload"] += "; REFERENCE ARM SAMPLE: " + res["sample"]
+    cfg["requested_nodes"] = args.nodes
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.nodes, None),
+        "steps": args.steps, "warmup": args.warmup, "steps_timed": res["steps_eq"], "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,14 +362,20 @@ def main_reference(args):
 
 
 def workload_config(args, n, nnz):
+    how = ("forced dt=%.3g (T=5 / 100 steps), one step = 6 RHS evals + stage algebra + error norm" % DT
+           if args.method == "dopri5" else
+           "fixed grid dt=%.3g, one step = %d RHS evals + stage algebra" % (DT, RHS_PER_STEP[args.method]))
+    rhs = {"ndcn": "relu((Phi X) W^T + b), Phi = norm. Laplacian", "heat": "k (-L) X  (HeatDiffusion)",
+           "gene": "-b x^f + A (x^h/(x^h+1))  (GeneDynamics)", "mutual": "MutualDynamics (edge-wise)"}[args.rhs]
     return {
-        "workload": "%s graph %d nodes (m=5 preferential attachment, %s order), Phi=norm. Laplacian CSR%s, hidden=%d, "
-                    "%s forced dt=%.3g (T=5 / 100 steps), one step = %d RHS evals + stage algebra + error norm"
-                    % (args.graph, n, args.layout, "" if nnz is None else " nnz=%d" % nnz, args.hidden, args.method, DT,
-                       RHS_PER_STEP[args.method]),
-        "nodes": n, "hidden": args.hidden, "method": args.method, "dt": DT,
+        "workload": "BASELINE config %s: %s graph %d nodes (%s order)%s, RHS %s, width=%d, %s %s"
+                    % (args.config or "north star", args.graph, n, args.layout, "" if nnz is None else " nnz=%d" % nnz,
+                       rhs, args.hidden, args.method, how),
+        "nodes": n, "hidden": args.hidden, "method": args.method, "dt": DT, "rhs": args.rhs,
         "l2_policy": "inputs larger than L2 (state %.0f MB x >=11 buffers vs 126 MB L2), no flush" %
-                     (n * args.hidden * 4 / 1e6),
+                     (n * args.hidden * 4 / 1e6) if n * args.hidden * 4 * 11 > (126 << 20) else
+                     "state %.1f MB x 11 buffers: 256 MB L2 flush buffer written between warm-up and timed region"
+                     % (n * args.hidden * 4 / 1e6),
     }
 
 
@@ -290,6 +409,15 @@ def pick_exchange(vols: dict, world: int, H: int, allow_push: bool = True) -> st
     return "halo"
 
 
+def solve_on(nb, graph, spec, y0, k, method):
+    """K forced steps on one GPU (the parity reference of the multi-GPU lines)."""
+    if method == "dopri5":
+        t = torch.tensor([0.0, DT * (k - 0.5)], dtype=torch.float64)
+        return nb.odeint_fused(graph, spec, y0, t, method="dopri5", forced_dt=DT, terminal_only=True)
+    t = torch.linspace(0, DT * k, k + 1, dtype=torch.float64)
+    return nb.odeint_fused(graph, spec, y0, t, method=method, terminal_only=True)
+
+
 # ----------------------------------------------------------------------------------------------
 def main_ours(args):
     import ndcn_b200 as nb
@@ -314,8 +442,17 @@ def main_ours(args):
     nnz = int(phi.nnz)
     W, b = make_weights(H)
     W, b = W.to(dev), b.to(dev)
-    spec = nb.RhsSpec.ndcn(H, W, b)
-    x0_host = make_state(n, H, pin=True)
+    if args.rhs == "ndcn":
+        spec = nb.RhsSpec.ndcn(H, W, b)
+    elif args.rhs == "heat":
+        spec = nb.RhsSpec.heat(H, 1.0)
+    elif args.rhs == "gene":
+        spec = nb.RhsSpec.gene(H, 1.0, 1.0, 2.0)
+    else:
+        spec = nb.RhsSpec.mutual(H)
+    if args.rhs != "ndcn" and world > 1:
+        raise RuntimeError("--rhs %s: the [N,d] ground-truth dynamics run as replicas (DESIGN.md section 6), --gpus 1" % args.rhs)
+    x0_host = make_state(n, H, pin=True, positive=args.rhs != "ndcn")
 
     z_block_cols = 0
     vols = None
@@ -398,8 +535,15 @@ def main_ours(args):
 
     out_buf = torch.empty((graph.n_rows, H), dtype=torch.float32, device=dev)
     # ---- warm-up (>= 3 steps, untimed) ----
-    solve(max(Wm, 1), x0, out=out_buf)
+    solve(max(Wm, 3), x0, out=out_buf)
     barrier()
+    small_state = n * H * 4 * 11 <= (126 << 20)
+    if small_state:
+        # the solver's buffers would sit in the 126 MB L2 after the warm-up: flush it with a 256 MB write
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush.fill_(1)
+        del flush
+        barrier()
 
     # ---- timed region: exactly K steps, state resident in HBM ----
     sampler = ClockSampler(local_rank)
@@ -409,7 +553,7 @@ def main_ours(args):
     barrier()
     wall0 = time.time()
     ev0.record()
-    yT = solve(K, x0, time_kernels=True, out=out_buf)
+    yT = solve(K, x0, out=out_buf)   # no per-launch instrumentation inside the region that produces `value`
     ev1.record()
     barrier()
     wall1 = time.time()
@@ -425,8 +569,21 @@ def main_ours(args):
     else:
         assert info.n_accepted == K and info.nfe == per_step * K + (1 if method == "dopri5" else 0), info
     finite = bool(torch.isfinite(yT).all())
+    y_keep = yT.clone() if world > 1 else None
     value = n * H * K / (ms * 1e-3)
     launches = int(info.n_launches)
+
+    # ---- the same K steps once more with CUDA events around every launch (NDCN_O_TIME_KERNELS): per-class device
+    # times for the roofline; this instrumented solve does not contribute to `value`
+    evi0, evi1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    evi0.record()
+    solve(K, x0, time_kernels=True, out=out_buf)
+    evi1.record()
+    barrier()
+    info_t = solver.last_solve_info
+    ms_instr = evi0.elapsed_time(evi1)
+    info = info_t
 
     # One RHS evaluation = the stage kernel (GEMM + bias/ReLU + RK epilogue; with the FP32-FMA family it
     # also contains the gather) plus, on the tcgen05 path, the chunk-major gather launch that feeds it.
@@ -438,7 +595,7 @@ def main_ours(args):
     n_rows_local = graph.n_rows
     slice_cols = z_block_cols or (part.Hc if (world > 1 and scheme == "fpush") else 0)
     nnz_local = graph.nnz if not slice_cols else nnz // world  # feature-sharded: every rank gathers all rows on 1/world of the columns
-    algo_bytes = bytes_rhs(n_rows_local, nnz_local, H)
+    algo_bytes = bytes_rhs(n_rows_local, nnz_local, H, args.rhs)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -466,9 +623,12 @@ def main_ours(args):
         "traffic": traffic,
         "kernel": (f"RHS evaluation = {gather_name} + tcgen05 3xTF32 GEMM with bias/ReLU "
                    "and RK stage epilogue (k_stage_gemm_umma); time = sum of the two launches") if split else
-                  "fused RHS stage kernel (CSR gather + W GEMM + bias/ReLU + RK stage epilogue)",
+                  ("fused RHS stage kernel (CSR gather + W GEMM + bias/ReLU + RK stage epilogue)" if args.rhs == "ndcn"
+                   else "fused ground-truth RHS stage kernel (k_stage_dyn1 / k_stage_dynv: CSR gather + pointwise "
+                        "dynamics + RK stage epilogue)"),
         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": rhs_avg_ms, "launches_timed": int(stage_n),
-        "share_of_step": (stage_ms + gather_ms) / ms if ms > 0 else None,
+        "share_of_step": (stage_ms + gather_ms) / ms_instr if ms_instr > 0 else None,
+        "instrumented_ms_per_step": ms_instr / max(K, 1),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
         "class_ms": {"stage": stage_ms, "gather": gather_ms, "algebra": info.class_ms[_ffi.K_ALGEBRA],
                      "control": info.class_ms[_ffi.K_CONTROL], "emit": info.class_ms[_ffi.K_EMIT],
@@ -487,10 +647,18 @@ def main_ours(args):
             from ndcn_b200 import workloads as wl
             # the reference's own operator format at scale: uncoalesced fp32 sparse COO (utils.py:12-23);
             # ODEFunc converts it to CSR on the GPU at its first use (the warm-up call below)
-            func = nb.ODEFunc(H, wl.to_reference_coo(phi))
-            func.wt.weight.data.copy_(W)
-            func.wt.bias.data.copy_(b)
-            func = func.to(dev).eval()
+            coo = wl.to_reference_coo(phi)
+            if args.rhs == "ndcn":
+                func = nb.ODEFunc(H, coo)
+                func.wt.weight.data.copy_(W)
+                func.wt.bias.data.copy_(b)
+                func = func.to(dev).eval()
+            elif args.rhs == "heat":
+                func = nb.HeatDiffusion(-coo, 1)  # the module negates its argument (heat_dynamics.py:190)
+            elif args.rhs == "gene":
+                func = nb.GeneDynamics(coo, 1)
+            else:
+                func = nb.MutualDynamics(coo)
             t_host = torch.tensor([0.0, DT * (K - 0.5)], dtype=torch.float64)
             opts = {"forced_dt": DT} if method == "dopri5" else None
             t_arg = t_host if method == "dopri5" else torch.linspace(0, DT * K, K + 1, dtype=torch.float64)
@@ -508,7 +676,7 @@ def main_ours(args):
             assert res.device.type == "cpu" and res.shape == (n, H)
             e2e = {"value": n * H * K / e_s, "unit": UNIT, "h2d_bytes_per_step": n * H * 4 / K,
                    "d2h_bytes_per_step": n * H * 4 / K, "seconds": e_s,
-                   "note": "one ndcn_b200.odeint(ODEFunc, y0_pinned_host, t) call covering K steps; y0 H2D (%d B) and "
+                   "note": "one ndcn_b200.odeint(func, y0_pinned_host, t) call covering K steps; y0 H2D (%d B) and "
                            "y(T) D2H (%d B) inside the timed region, bytes amortised over K steps" % (n * H * 4, n * H * 4)}
         else:
             # multi-GPU e2e: every rank stages its row block from pinned host memory and returns it
@@ -563,11 +731,54 @@ def main_ours(args):
         except Exception as exc:  # diagnostics only: never cost the bench line
             line["partition"]["class_ms_per_step_by_rank"] = "unavailable: %s" % (exc,)
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del x0, out_buf
+    # ---- multi-GPU parity: the K-step result against the single-GPU solve of the same steps (rank 0 runs it on the
+    # whole graph), on every 64th row of every rank's block.  A line whose result is off is not printed as a result.
+    if world > 1 and not args.no_parity and not args.adaptive:
+        try:
+            idx = torch.arange(0, graph.n_rows, 64, device=dev)
+            mine_rows = y_keep.index_select(0, idx).cpu()
+            gathered = [None] * world
+            dist.gather_object((int(part.row0), idx.cpu(), mine_rows), gathered if rank == 0 else None, dst=0)
+            parity = None
+            if rank == 0:
+                g1 = nb.CsrGraph.from_scipy(phi, dev)
+                y_ref = solve_on(nb, g1, spec, x0_host.to(dev), K, method)
+                worst, worst_rel, n_cmp = 0.0, 0.0, 0
+                for row0, ii, rows in gathered:
+                    ref = y_ref.index_select(0, (ii + row0).to(dev)).cpu()
+                    d = (rows - ref).abs()
+                    worst = max(worst, float(d.max()))
+                    worst_rel = max(worst_rel, float((d / (1e-5 + 1e-4 * ref.abs())).max()))
+                    n_cmp += rows.numel()
+                parity = {"reference": "single-GPU solve of the same %d forced steps on rank 0" % K,
+                          "rows_compared": n_cmp // H, "max_abs_diff": worst,
+                          "max_violation_of_rtol1e-4_atol1e-5": worst_rel, "ok": bool(worst_rel <= 1.0)}
+                del y_ref, g1
+            box = [parity]
+            dist.broadcast_object_list(box, src=0)
+            line["parity"] = box[0]
+        except Exception as exc:
+            line["parity"] = {"ok": False, "error": repr(exc)}
+        if not line["parity"].get("ok", False):
+            line["value"] = None
+            line["invalid"] = "multi-GPU result differs from the single-GPU solve: see parity"
+
+    if rank == 0 and world == 1 and args.rhs == "ndcn" and not (args.no_cpu_baseline and args.no_gpu_baseline):
+        del x0, out_buf, yT
+        solver.release_workspaces()
         torch.cuda.empty_cache()
-        res = cpu_reference_run(args, 2, 1, args.cpu_budget_s)
-        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_gpu_baseline:
+            # the reference's own GPU path on this B200 (cuSPARSE SpMM on the uncoalesced COO operator, cuBLAS Linear,
+            # ~123 Python-issued elementwise kernels per dopri5 step): the existing GPU path the fused kernels replace
+            try:
+                res = reference_run(args, dev, 1e9, n_fixed=n)
+                line["gpu_baseline"] = {k: res[k] for k in ("value", "unit", "kind", "sample", "ms_per_step")}
+            except Exception as exc:  # e.g. out of memory in torch.sparse.mm's coalesce at 4M nodes
+                line["gpu_baseline"] = {"unavailable": repr(exc)[:300]}
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            res = reference_run(args, torch.device("cpu"), args.cpu_budget_s)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line))
     if peers is not None:

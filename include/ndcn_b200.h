@@ -294,6 +294,10 @@ int64_t ndcn_config_get(int32_t key);
 int ndcn_debug_umma_trace(void* buf_dev);
 
 /* library / build information */
+/* sizeof() of the structs the library reads or writes, so that a binding can check its own declarations:
+ * 0 ndcn_rhs_desc_t, 1 ndcn_solve_opts_t, 2 ndcn_solve_stats_t, 3 ndcn_peer_config_t,
+ * 4 ndcn_feature_peer_config_t, 5 ndcn_gather_request_t; anything else: -1 */
+int ndcn_sizeof(int32_t which);
 const char* ndcn_version(void);
 int ndcn_sm_arch(void); /* 100: built for sm_100a */
 

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "ndcn_config_set": (C.c_int, [C.c_int32, C.c_int64]),
     "ndcn_config_get": (C.c_int64, [C.c_int32]),
     "ndcn_debug_umma_trace": (C.c_int, [C.c_void_p]),
+    "ndcn_sizeof": (C.c_int, [C.c_int32]),
     "ndcn_version": (C.c_char_p, []),
     "ndcn_sm_arch": (C.c_int, []),
 }

@@ -116,6 +116,35 @@ static const double kDpMid[7] = {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+// SM count of the current device (148 on B200), queried once per device
+static int sm_count_now() {
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+// cudaFuncSetAttribute is per device: remember it per (kernel instantiation, device)
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool; with the
 // default release threshold of 0 the pool hands its memory back to the OS at every synchronisation
 // and the next allocation pays for a fresh mapping (~100 us).  Keep freed scratch in the pool.
@@ -201,25 +230,25 @@ static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaSt
     *grid_out = grid;
     // H=256: 4 CTAs/SM (64 registers) x 4 row loads in flight per lane measured best on B200
     // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
-    // H=256: 4 CTAs/SM (64 registers) x 4 row loads in flight per lane measured best on B200
-    // (1.69 ms vs 1.86 ms at 3 CTAs/SM for the 1M-node power-law gather, profiles/README.md)
+    // plain z = Phi x feeding the tcgen05 GEMM kernel: the instantiation without the stage algebra
+    const bool store_only = e.mode == EPI_STORE && e.feat_mode == FEAT_OFF && e.k_out.p[0] != nullptr && !(a.flags & NDCN_F_NO_GRAPH);
     if constexpr (VW == 4 && NCH == 2) {
-      k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
+      if (store_only) k_stage_ndcn_row<VW, NCH, 4, 4, true><<<grid, kStageThreads, 0, st>>>(a, e);
+      else k_stage_ndcn_row<VW, NCH, 4, 4><<<grid, kStageThreads, 0, st>>>(a, e);
     } else if constexpr (VW == 4 && NCH == 1) {
       // H=128: 8 row loads in flight per lane at 5 CTAs/SM measured best (0.98 ms vs 1.34 ms for the
       // default instantiation on the 1M-node power-law gather)
-      k_stage_ndcn_row<VW, NCH, 8, 5><<<grid, kStageThreads, 0, st>>>(a, e);
+      if (store_only) k_stage_ndcn_row<VW, NCH, 8, 5, true><<<grid, kStageThreads, 0, st>>>(a, e);
+      else k_stage_ndcn_row<VW, NCH, 8, 5><<<grid, kStageThreads, 0, st>>>(a, e);
     } else {
       k_stage_ndcn_row<VW, NCH><<<grid, kStageThreads, 0, st>>>(a, e);
     }
   } else {
     using S = GemmSmem<VW, NCH>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need())
       CU_TRY(cudaFuncSetAttribute(k_stage_ndcn_gemm<VW, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)S::total));
-      attr_set = true;
-    }
     const int grid = (int)((n + kTileRows - 1) / kTileRows);
     *grid_out = grid;
     k_stage_ndcn_gemm<VW, NCH><<<grid, kStageThreads, S::total, st>>>(a, e);
@@ -360,12 +389,10 @@ static int launch_gather(const RhsBinding& b, const NdcnArgs& a, int H, EpiArgs&
 template <int H, int MODE, int NPREV, int B>
 static int launch_umma_inst(const UmmaArgs& u, EpiArgs& e, int grid, cudaStream_t st) {
   using Cf = UmmaCfg<H>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.need())
     CU_TRY(cudaFuncSetAttribute(k_stage_gemm_umma<H, MODE, NPREV, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)Cf::kSmemBytes));
-    attr_set = true;
-  }
   k_stage_gemm_umma<H, MODE, NPREV, B><<<grid, kUmmaThreads, Cf::kSmemBytes, st>>>(u, e);
   return (int)cudaGetLastError();
 }
@@ -392,8 +419,15 @@ static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_ou
         case 5: NDCN_UMMA_CASE(EPI_LINCOMB, 5, 1, 2);
         default: return NDCN_E_ARG;
       }
+    case EPI_LINCOMB_E:
+      switch (e.n_prev) {
+        case 4: NDCN_UMMA_CASE(EPI_LINCOMB_E, 4, 1, 2);
+        case 5: NDCN_UMMA_CASE(EPI_LINCOMB_E, 5, 1, 2);
+        default: return NDCN_E_ARG;
+      }
     case EPI_ERR:
       switch (e.n_prev) {
+        case 1: NDCN_UMMA_CASE(EPI_ERR, 1, 2, 1);
         case 5: NDCN_UMMA_CASE(EPI_ERR, 5, 1, 2);
         case 6: NDCN_UMMA_CASE(EPI_ERR, 6, 1, 2);
         default: return NDCN_E_ARG;
@@ -425,18 +459,22 @@ static EpiArgs store_only(float* out);
 // non-finite k_j would make the product NaN, and such a k_j has already poisoned the stage inputs
 // built from it with non-zero coefficients, so the non-finite guard fires either way.)
 static void drop_zero_terms(EpiArgs& e) {
-  if (e.mode != EPI_LINCOMB && e.mode != EPI_ERR) return;
-  if (e.n_prev < 2) return;
+  if (e.mode != EPI_LINCOMB && e.mode != EPI_ERR && e.mode != EPI_LINCOMB_E) return;
+  if (e.n_prev < 2 || e.err_prefix) return;
+  const bool two = e.mode == EPI_LINCOMB_E;  // a stream is skipped only if BOTH sums carry a zero for it
   int w = 0;
   for (int j = 0; j < e.n_prev; ++j) {
-    if (e.beta[j] == 0.0f && !(w == 0 && j == e.n_prev - 1)) continue;  // keep at least one earlier term
+    const bool zero = e.beta[j] == 0.0f && (!two || e.ebeta[j] == 0.0f);
+    if (zero && !(w == 0 && j == e.n_prev - 1)) continue;  // keep at least one earlier term
     e.kprev[w] = e.kprev[j];
     e.beta[w] = e.beta[j];
+    e.ebeta[w] = e.ebeta[j];
     ++w;
   }
   if (w == e.n_prev) return;
   e.beta[w] = e.beta[e.n_prev];  // coefficient of the fresh k
-  for (int j = w + 1; j < 8; ++j) e.beta[j] = 0.0f;
+  e.ebeta[w] = e.ebeta[e.n_prev];
+  for (int j = w + 1; j < 8; ++j) e.beta[j] = e.ebeta[j] = 0.0f;
   e.n_prev = w;
 }
 
@@ -552,7 +590,7 @@ static int max_partials_for(const ndcn_graph* g, int H) {
   const int64_t n_rows = g->v.n_rows;
   int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32) + g->n_long;
   int64_t by_lpr4 = (n_rows + 63) / 64;
-  int64_t best = std::max<int64_t>(std::max(by_rows, by_lpr4), 148 * 16);
+  int64_t best = std::max<int64_t>(std::max(by_rows, by_lpr4), (int64_t)sm_count_now() * 16);  // grid_for_elems' cap
   if (H % 16 == 0) {
     const int cws[3] = {16, 32, 64};
     for (int cw : cws)
@@ -659,12 +697,7 @@ extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* r
     if (rhs->H == 256) prep_w_image<256>(rhs->W, Wimg, st);
     else prep_w_image<128>(rhs->W, Wimg, st);
   }
-  RhsBinding b{g, rhs, Wt, nullptr, 0, 148};
-  cudaDeviceGetAttribute(&b.sm_count, cudaDevAttrMultiProcessorCount, 0);
-  {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&b.sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
+  RhsBinding b{g, rhs, Wt, nullptr, 0, sm_count_now()};
   // without Z the dispatcher falls back to the SIMT kernels; no_graph needs no Z: give it a non-null tag
   b.Z = use_umma ? (Z ? Z : out) : nullptr;
   b.Wimg = Wimg;
@@ -695,11 +728,7 @@ extern "C" int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, 
   if (!no_control && (!rhs->W || !rhs->b)) return NDCN_E_ARG;
   if (n == 0) return NDCN_OK;
   cudaStream_t st = (cudaStream_t)s;
-  int sm_count = 148;
-  {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sm_count = sm_count_now();
   const int64_t numel = n * H;
   const bool vec = aligned16(x) && aligned16(gk) && aligned16(gx) && aligned16(gp) && (!z || aligned16(z)) && H % 4 == 0;
   auto elementwise = [&](const float* k_in, EpiArgs e) {
@@ -865,9 +894,7 @@ extern "C" int ndcn_solver_create(const ndcn_graph_t* g, const ndcn_rhs_desc_t* 
     p = (unsigned char*)align_up((size_t)p, 1024);
     sv->Wimg = take(align_up(sizeof(float) * 2 * (size_t)sv->H * sv->H, 1024));
   }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sv->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  sv->sm_count = sm_count_now();
   sv->max_partials = max_partials_for(g, sv->H);
   int rc = (int)cudaMalloc((void**)&sv->partials, sizeof(double) * 2 * sv->max_partials);
   if (!rc) rc = (int)cudaMalloc((void**)&sv->xchg, sizeof(double) * 4);
@@ -1189,6 +1216,7 @@ struct Dopri {
   EmitArgs emit;
   bool host_parity;  // hooks need the host to know the buffer parity: poll every attempt
   int par = 0;
+  bool err_prefix = true;  // stage 5 leaves the error-estimate prefix behind (NDCN_ERR_PREFIX=0: off, A/B runs)
 
   explicit Dopri(Driver& dr) : d(dr), sv(dr.sv) {
     std::memset(beta32, 0, sizeof(beta32));
@@ -1196,6 +1224,7 @@ struct Dopri {
     for (int s = 0; s < 6; ++s)
       for (int j = 0; j <= s; ++j) beta32[s][j] = (float)kDpBeta[s][j];
     for (int j = 0; j < 7; ++j) err32[j] = (float)kDpErr[j];
+    if (const char* v = std::getenv("NDCN_ERR_PREFIX")) err_prefix = std::atoi(v) != 0;
   }
 
   int reduce_and_control(int n_partials) {
@@ -1239,13 +1268,29 @@ struct Dopri {
       e.k_out = pp(sv->K[s - 1]);
       if (s >= 2) e.kprev[s - 1] = pp(sv->K[s - 2]);
       e.y_out = (s < 5) ? pp(sv->YS[s & 1]) : Yoth;  // stage 5 forms y1 (FSAL: c_sol == beta[-1])
+      if (s == 5 && err_prefix) {
+        // this stage reads k1..k5 and holds k6: it also leaves sum_{j<=6} (dt*c_err_j) k_j (the left-to-right prefix
+        // of rk_common.py:60) in YS[1] (own rows; free since stage 4 consumed it), so the error stage reads 1 stream, not 6
+        e.mode = EPI_LINCOMB_E;
+        e.e_out = sv->YS[1];
+        for (int j = 0; j < 8; ++j) e.ebeta[j] = j < 6 ? err32[j] : 0.0f;
+      }
       RC_TRY(d.stage(pp(src), src, e, sv->K[s - 1]));
     }
     // stage 6: k7 = f(y1) + error estimate
     e.mode = EPI_ERR;
-    e.n_prev = 6;
-    for (int j = 0; j < 8; ++j) e.beta[j] = err32[j];
-    e.kprev[5] = pp(sv->K[4]);
+    e.e_out = nullptr;
+    if (err_prefix) {
+      e.n_prev = 1;
+      e.err_prefix = 1;
+      for (int j = 0; j < 8; ++j) e.beta[j] = 0.0f;
+      e.beta[1] = err32[6];
+      e.kprev[0] = pp(sv->YS[1]);
+    } else {
+      e.n_prev = 6;
+      for (int j = 0; j < 8; ++j) e.beta[j] = err32[j];
+      e.kprev[5] = pp(sv->K[4]);
+    }
     e.k_out = KFoth;
     e.y_out = pp(nullptr);
     e.y1 = Yoth;
@@ -1357,6 +1402,7 @@ struct Dopri {
     if (!forced && !given_first) {
       // _select_initial_step(order=4)     dopri5.py:80, misc.py:84-143
       const int grid = grid_for_elems(sv->numel, sv->sm_count);
+      if (grid > sv->max_partials) return NDCN_E_WORKSPACE;  // k_init_norms writes 2 doubles per CTA
       sv->launches += 1;
       k_init_norms<<<grid, kStageThreads, 0, st>>>(sv->Y[0], sv->KF[0], nullptr, sv->numel, (float)d.o->rtol,
                                                     (float)d.o->atol, 0, sv->partials);
@@ -1634,7 +1680,7 @@ extern "C" int ndcn_rk_combine_f32(float* out, const float* y0, const float* con
   for (int j = 0; j < n_k; ++j) e.beta[j] = (float)beta_host[j];
   bool vec = aligned16(out) && aligned16(y0) && numel % 4 == 0;
   for (int j = 0; j < n_k; ++j) vec = vec && aligned16(k_host_ptrs[j]);
-  k_epi_only<<<grid_for_elems(numel, 148), kStageThreads, 0, st>>>(pp(const_cast<float*>(k_host_ptrs[n_k - 1])), numel, e,
+  k_epi_only<<<grid_for_elems(numel, sm_count_now()), kStageThreads, 0, st>>>(pp(const_cast<float*>(k_host_ptrs[n_k - 1])), numel, e,
                                                                   vec ? 1 : 0);
   return (int)cudaGetLastError();
 }
@@ -1643,7 +1689,7 @@ extern "C" int ndcn_error_ratio_f32(const float* err, const float* y0, const flo
                                     int64_t numel, double* sum_out_dev, ndcn_stream_t s) {
   if (!err || !y0 || !y1 || !sum_out_dev || numel < 0) return NDCN_E_ARG;
   cudaStream_t st = (cudaStream_t)s;
-  const int grid = grid_for_elems(numel, 148);
+  const int grid = grid_for_elems(numel, sm_count_now());
   double* partials = nullptr;
   CU_TRY(cudaMallocAsync((void**)&partials, sizeof(double) * grid, st));
   k_error_ratio<<<grid, kStageThreads, 0, st>>>(err, y0, y1, numel, (float)rtol, (float)atol, partials);
@@ -1658,7 +1704,7 @@ extern "C" int ndcn_pack_rows_f32(const float* x, const int32_t* idx, int64_t n_
   if (n_idx == 0) return NDCN_OK;
   const int vec = (H % 4 == 0) && aligned16(x) && aligned16(out);
   const int64_t blocks = (n_idx + kWarpsPerCta - 1) / kWarpsPerCta;
-  const int grid = (int)std::min<int64_t>(blocks, 148 * 16);
+  const int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count_now() * 16);
   k_pack_rows<<<grid, kStageThreads, 0, (cudaStream_t)s>>>(x, idx, n_idx, H, out, vec);
   return (int)cudaGetLastError();
 }
@@ -1669,7 +1715,7 @@ extern "C" int ndcn_pack_cols_f32(const float* x, int64_t n_rows, int32_t H, int
   if (n_rows == 0) return NDCN_OK;
   if (!x || !out || !aligned16(x) || !aligned16(out)) return NDCN_E_ARG;
   const int64_t n4 = n_rows * (H / 4);
-  const int grid = (int)std::min<int64_t>((n4 + kStageThreads - 1) / kStageThreads, 148 * 16);
+  const int grid = (int)std::min<int64_t>((n4 + kStageThreads - 1) / kStageThreads, (int64_t)sm_count_now() * 16);
   k_pack_cols<<<grid, kStageThreads, 0, (cudaStream_t)s>>>(x, n_rows, H, block_cols, out);
   return (int)cudaGetLastError();
 }
@@ -1677,6 +1723,18 @@ extern "C" int ndcn_pack_cols_f32(const float* x, int64_t n_rows, int32_t H, int
 extern "C" int ndcn_debug_umma_trace(void* buf_dev) {
   unsigned long long* p = (unsigned long long*)buf_dev;
   return (int)cudaMemcpyToSymbol(g_umma_trace, &p, sizeof(p));
+}
+
+extern "C" int ndcn_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int)sizeof(ndcn_rhs_desc_t);
+    case 1: return (int)sizeof(ndcn_solve_opts_t);
+    case 2: return (int)sizeof(ndcn_solve_stats_t);
+    case 3: return (int)sizeof(ndcn_peer_config_t);
+    case 4: return (int)sizeof(ndcn_feature_peer_config_t);
+    case 5: return (int)sizeof(ndcn_gather_request_t);
+    default: return -1;
+  }
 }
 
 extern "C" const char* ndcn_version(void) { return "ndcn_b200 0.1.0 (sm_100a)"; }

@@ -53,6 +53,10 @@ enum EpiMode : int {
   EPI_RK4_3 = 5,    // y + dt*(k1 - k2 + k3)                      (rk_common.py:77)
   EPI_RK4_4 = 6,    // y + (k1 + 3k2 + 3k3 + k4)*(dt/8)           (rk_common.py:78, solvers.py:91)
   EPI_MASK = 7,     // backward of the ReLU: y_out = k > 0 ? (dt*beta_0) * aux : 0, aux read through y0
+  // EPI_LINCOMB that also writes e_out = sum_j (dt*ebeta_j) k_j over the same k_j (fresh k last): dopri5's last
+  // Runge-Kutta stage holds k1..k6 anyway, so it leaves the left-to-right PREFIX of the error estimate
+  // (rk_common.py:60) behind and the error stage reads one stream instead of six (EpiArgs::err_prefix)
+  EPI_LINCOMB_E = 8,
 };
 
 enum DtSrc : int { DT_HOST = 0, DT_CTRL = 1, DT_CTRL_H0 = 2 };
@@ -96,6 +100,11 @@ struct EpiArgs {
   int feat_rank;
   int feat_row0;        // first global row of this rank's block
   int feat_hc_log2, feat_h_log2;
+  // EPI_LINCOMB_E: second coefficient set and its output; EPI_ERR with err_prefix: kprev[0] already holds
+  // sum_{j<6} (dt*c_err_j) k_j and is added as it is
+  float* e_out;
+  float ebeta[8];
+  int err_prefix;
 };
 
 struct EpiCtx {  // EpiArgs resolved against the controller, per thread
@@ -113,6 +122,10 @@ struct EpiCtx {  // EpiArgs resolved against the controller, per thread
   long long peer_delta[kMaxPeers];
   const FeatTable* feat;
   int feat_mode, feat_rank, feat_row0, feat_hc_log2, feat_h_log2;
+  float* e_out;
+  float ecoef[8];
+  float ecoef_fresh;
+  int err_prefix;
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -164,6 +177,11 @@ __device__ __forceinline__ bool epi_resolve(const EpiArgs& a, EpiCtx& c) {
   c.feat_row0 = a.feat_row0;
   c.feat_hc_log2 = a.feat_hc_log2;
   c.feat_h_log2 = a.feat_h_log2;
+  c.e_out = a.e_out;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c.ecoef[j] = fmul(dt, a.ebeta[j]);
+  c.ecoef_fresh = fmul(dt, a.ebeta[a.n_prev & 7]);
+  c.err_prefix = a.err_prefix;
   return true;
 }
 
@@ -305,7 +323,30 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
     store_z_owner<VW>(c.feat, c.feat_rank, c.feat_hc_log2, off, k[0], k[VW > 1 ? 1 : 0], k[VW > 2 ? 2 : 0], k[VW > 3 ? 3 : 0]);
   if (c.mode == EPI_STORE) return;
 
-  if (c.mode == EPI_LINCOMB) {
+  if (c.mode == EPI_LINCOMB || c.mode == EPI_LINCOMB_E) {
+    if (c.mode == EPI_LINCOMB_E) {
+      // prefix of the error estimate over the same stages, same summation order as EPI_ERR below
+      float ea[VW];
+      if (c.n_prev == 0) {
+#pragma unroll
+        for (int i = 0; i < VW; ++i) ea[i] = fmul(c.ecoef[0], k[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VW; ++i) ea[i] = fmul(c.ecoef[0], in.kp[0][i]);
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+          if (j < c.n_prev) {
+#pragma unroll
+            for (int i = 0; i < VW; ++i) ea[i] = fadd(ea[i], fmul(c.ecoef[j], in.kp[j][i]));
+          }
+        }
+        const float ef = c.ecoef_fresh;
+#pragma unroll
+        for (int i = 0; i < VW; ++i) ea[i] = fadd(ea[i], fmul(ef, k[i]));
+      }
+      if (stream_out) stv_stream<VW>(c.e_out + off, ea);
+      else stv<VW>(c.e_out + off, ea);
+    }
     // y_out = y0 + sum_j (dt*beta_j) k_j, summed left to right from the first term
     // (misc.py:22-25: sum() of the per-term products; rk_common.py:50)
     float acc[VW];
@@ -338,7 +379,7 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
     // ratio = err / (atol + rtol*max(|y0|,|y1|)); sum ratio^2      misc.py:146-157
     float acc[VW];
 #pragma unroll
-    for (int i = 0; i < VW; ++i) acc[i] = fmul(c.coef[0], in.kp[0][i]);
+    for (int i = 0; i < VW; ++i) acc[i] = c.err_prefix ? in.kp[0][i] : fmul(c.coef[0], in.kp[0][i]);
 #pragma unroll
     for (int j = 1; j < 6; ++j) {
       if (j < c.n_prev) {

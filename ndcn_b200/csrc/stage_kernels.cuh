@@ -106,19 +106,30 @@ struct NdcnArgs {
 // after every other row is done: rows above kLongRow entries are skipped by the row-per-warp
 // CTAs and handled by the first n_long CTAs of the grid, whose 8 warps interleave 32-entry
 // batches of the row and add their partial sums in warp order (fixed, reproducible).
-template <int VW, int NCH, int U = 4, int MINB = 3>
+// STORE_ONLY: the epilogue is a plain streaming store of z = Phi x into e.k_out (what feeds the tcgen05 GEMM
+// kernel); none of the stage algebra's pointers and coefficients then occupies registers.
+template <int VW, int NCH, int U = 4, int MINB = 3, bool STORE_ONLY = false>
 __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs a, EpiArgs e) {
   constexpr int H = 32 * VW * NCH;
   __shared__ float s_part[kWarpsPerCta][H];
   EpiCtx c;
-  if (!epi_resolve(e, c)) return;
+  if constexpr (STORE_ONLY) {
+    if (e.ctrl != nullptr && ((volatile Ctrl*)e.ctrl)->done) return;
+  } else {
+    if (!epi_resolve(e, c)) return;
+  }
   const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
   const float* __restrict__ x = sel(a.x, par);
+  float* __restrict__ zout = STORE_ONLY ? sel(e.k_out, par) : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool relu = !(a.flags & NDCN_F_NO_RELU);
   const bool graph = !(a.flags & NDCN_F_NO_GRAPH);
   const int n_long = graph ? a.n_long : 0;
   double err_acc = 0.0;
+  auto finish = [&](int64_t off, float (&v)[VW]) {
+    if constexpr (STORE_ONLY) stv_stream<VW>(zout + off, v);
+    else epi_apply<VW>(c, off, v, err_acc);
+  };
   if ((int)blockIdx.x < n_long) {
     const int64_t row = __ldg(a.long_rows + blockIdx.x);
     const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs
 #pragma unroll
           for (int i = 0; i < VW; ++i) tot[i] = fmaxf(tot[i], 0.f);
         }
-        epi_apply<VW>(c, row * H + ch * 32 * VW + lane * VW, tot, err_acc);
+        finish(row * H + ch * 32 * VW + lane * VW, tot);
       }
     }
   } else {
@@ -166,12 +177,12 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs
 #pragma unroll
             for (int i = 0; i < VW; ++i) acc[ch][i] = fmaxf(acc[ch][i], 0.f);
           }
-          epi_apply<VW>(c, row * H + ch * 32 * VW + lane * VW, acc[ch], err_acc);
+          finish(row * H + ch * 32 * VW + lane * VW, acc[ch]);
         }
       }
     }
   }
-  epi_finish_block(e, err_acc);
+  if constexpr (!STORE_ONLY) epi_finish_block(e, err_acc);
 }
 
 // ---------------------------------------------------------------------------------------

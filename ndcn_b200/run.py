@@ -65,17 +65,45 @@ def install(script_dir: str) -> None:
         del sys.modules[name]
 
 
+def run_script(argv, seed=None, run_name="__main__"):
+    """Run the unmodified script ``argv[0]`` with arguments ``argv[1:]`` on this backend; returns the
+    script's module globals (``solution_numerical``, ``model``, ... for the dynamics scripts).
+
+    ``seed``: the dynamics scripts never seed torch (heat_dynamics.py:82,89 seed only networkx), so two runs
+    differ in their weight initialisation; a seed given here (or NDCN_RUN_SEED in the environment) is applied
+    to torch and numpy BEFORE the script starts -- the script itself stays untouched."""
+    script = os.path.abspath(argv[0])
+    _env_shims()
+    install(os.path.dirname(script))
+    if seed is None and os.environ.get("NDCN_RUN_SEED"):
+        seed = int(os.environ["NDCN_RUN_SEED"])
+    if seed is not None:
+        import numpy as np
+        import torch
+
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+    old_argv, old_cwd = sys.argv, os.getcwd()
+    sys.argv = [script] + list(argv[1:])
+    os.chdir(os.path.dirname(script))  # dgnn.py reads data/<dataset>/... relative to cwd (utils.py:122)
+    try:
+        return runpy.run_path(script, run_name=run_name)
+    finally:
+        sys.argv = old_argv
+        os.chdir(old_cwd)
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
         print(__doc__)
         return 2
-    script = os.path.abspath(argv[0])
-    _env_shims()
-    install(os.path.dirname(script))
-    sys.argv = [script] + argv[1:]
-    os.chdir(os.path.dirname(script))  # dgnn.py reads data/<dataset>/... relative to cwd (utils.py:122)
-    runpy.run_path(script, run_name="__main__")
+    g = run_script(argv)
+    save = os.environ.get("NDCN_RUN_SAVE")  # test hook: persist the ground-truth tensor the script integrated
+    if save and "solution_numerical" in g:
+        import numpy as np
+
+        np.save(save, g["solution_numerical"].detach().cpu().numpy())
     return 0
 
 

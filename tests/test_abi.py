@@ -67,6 +67,35 @@ def test_peer_api_argument_validation_without_gpu():
     assert ctypes.sizeof(_ffi.FeaturePeerConfig) == 8 + 3 * 8 * 8 + 9 * 8
 
 
+def test_struct_sizes_match_the_library():
+    """every ctypes struct of the binding has the size the C side compiled with (ndcn_sizeof)"""
+    lib = _ffi.lib()
+    for which, cls in enumerate([_ffi.RhsDesc, _ffi.SolveOpts, _ffi.SolveStats, _ffi.PeerConfig,
+                                 _ffi.FeaturePeerConfig, _ffi.GatherRequest]):
+        assert ctypes.sizeof(cls) == lib.ndcn_sizeof(which), cls.__name__
+    assert lib.ndcn_sizeof(99) == -1
+
+
+def test_integration_md_stub_structs_match_the_library():
+    """INTEGRATION.md's binding stub declares the same struct layouts as include/ndcn_b200.h (a stale stub would
+    make the library read past the caller's struct)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes as C, torch.*?)```", text, flags=re.S).group(1)
+    lib = _ffi.lib()
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)  # the stub loads the library by its in-tree relative path
+    try:
+        exec(compile(block, "INTEGRATION.md", "exec"), ns)  # its own asserts compare against ndcn_sizeof
+    finally:
+        os.chdir(cwd)
+    assert ctypes.sizeof(ns["RhsDesc"]) == lib.ndcn_sizeof(0)
+    assert ctypes.sizeof(ns["SolveOpts"]) == lib.ndcn_sizeof(1)
+    assert ctypes.sizeof(ns["SolveStats"]) == lib.ndcn_sizeof(2)
+    fields = [f[0] for f in ns["SolveOpts"]._fields_]
+    assert fields == [f[0] for f in _ffi.SolveOpts._fields_]
+
+
 def test_sass_has_bulk_copy_and_no_legacy_paths():
     """The W^T chunks move with cp.async.bulk (SASS UBLKCP); built for sm_100a only."""
     import shutil
