@@ -12,8 +12,14 @@ Operator definitions follow the reference:
   norm_adj  D^-1/2 A D^-1/2            utils_in_learn_dynamics.py:123-134
   kipf      (D+I)^-1/2 (A+I) (D+I)^-1/2   utils_in_learn_dynamics.py:80-92
   lap       D - A                       heat_dynamics.py:116-117
+  alpha     (aI+(1-a)D)^-1/2 (aI+(1-a)A) (aI+(1-a)D)^-1/2   propagation.py:91-103 -- what dgnn.py runs on
+            (utils.py:204-211, ``--alpha``, default .5; README flags use 0: the plain normalized adjacency)
 with D^-1/2 := 0 on isolated nodes (the reference leaves those entries uninitialised,
 utils_in_learn_dynamics.py:117-118).
+
+Node orderings (``reorder``): the reference's ``--layout degree | community``
+(utils_in_learn_dynamics.py:212-247) and, for graphs beyond networkx's reach, reverse Cuthill-McKee and
+breadth-first orders from scipy.sparse.csgraph (gather locality / halo size of a row partition).
 """
 from __future__ import annotations
 
@@ -121,7 +127,50 @@ def _inv_sqrt(deg: np.ndarray) -> np.ndarray:
     return out
 
 
-def graph_operator(a: sp.csr_matrix, kind: str = "norm_lap") -> sp.csr_matrix:
+def reorder(a: sp.csr_matrix, kind: str = "degree") -> Tuple[sp.csr_matrix, np.ndarray]:
+    """Permuted adjacency and ``order`` (order[new_id] = old_id).
+
+    ``degree``     decreasing degree, ties in node order (generate_node_mapping, utils_in_learn_dynamics.py:218-220)
+    ``community``  greedy-modularity communities one after the other, largest first, members in networkx's set
+                   order (:221-226; networkx, so a few 10k nodes at most)
+    ``rcm``        reverse Cuthill-McKee (bandwidth reduction; scales to millions of nodes)
+    ``bfs``        breadth-first order from the highest-degree node
+    """
+    n = a.shape[0]
+    if kind == "degree":
+        return reorder_by_degree(a)
+    if kind == "community":
+        import networkx as nx
+        from networkx.algorithms import community
+
+        g = nx.from_scipy_sparse_array(a)
+        order = np.array([v for c in community.greedy_modularity_communities(g) for v in c], dtype=np.int64)
+    elif kind == "rcm":
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+        order = np.asarray(reverse_cuthill_mckee(a.tocsr(), symmetric_mode=True), dtype=np.int64)
+    elif kind == "bfs":
+        from scipy.sparse.csgraph import breadth_first_order
+
+        deg = np.asarray(a.sum(1)).ravel()
+        seen = np.zeros(n, bool)
+        parts = []
+        for start in np.argsort(-deg, kind="stable"):  # one tree per connected component
+            if seen[start]:
+                continue
+            o = breadth_first_order(a, int(start), directed=False, return_predecessors=False)
+            seen[o] = True
+            parts.append(o.astype(np.int64))
+        order = np.concatenate(parts)
+    else:
+        raise ValueError("unknown ordering %r" % (kind,))
+    assert len(order) == n and len(np.unique(order)) == n
+    p = a[order][:, order].tocsr()
+    p.sort_indices()
+    return p, order
+
+
+def graph_operator(a: sp.csr_matrix, kind: str = "norm_lap", alpha: float = 0.5) -> sp.csr_matrix:
     """fp32 CSR of the chosen operator (see module docstring)."""
     n = a.shape[0]
     a = a.astype(np.float32).tocsr()
@@ -138,6 +187,12 @@ def graph_operator(a: sp.csr_matrix, kind: str = "norm_lap") -> sp.csr_matrix:
     elif kind == "norm_lap":
         d = sp.diags(_inv_sqrt(deg))
         m = eye - d @ a @ d
+    elif kind == "alpha":
+        # propagation.py:91-103: degrees of A' = a I + (1-a) A taken in fp32, rows and columns scaled separately
+        ap = (alpha * eye.astype(np.float64) + (1.0 - alpha) * a.astype(np.float64)).tocsr()
+        out_deg = np.asarray(ap.sum(1), dtype=np.float32).ravel()
+        in_deg = np.asarray(ap.sum(0), dtype=np.float32).ravel()
+        m = sp.diags(_inv_sqrt(out_deg).astype(np.float64)) @ ap @ sp.diags(_inv_sqrt(in_deg).astype(np.float64))
     else:
         raise ValueError("unknown operator %r" % (kind,))
     m = m.tocsr().astype(np.float32)

@@ -58,6 +58,8 @@ def test_duck_typed_script_classes(golden):
             super().__init__()
             self.A, self.b, self.f, self.h = A, b, f, h
 
+        ndcn_b200_fused = True  # opt in: this forward is not the reference's source, so say it computes the same
+
         def forward(self, t, x):
             raise AssertionError("the fused path must not call back into Python")
 
@@ -303,3 +305,59 @@ def test_rhs_vjp_primitive(impl, flags):
     gx64 = base.double() + (u64 if kw["no_graph"] else A64.t() @ u64)
     err = float((gx.double() - gx64).norm() / gx64.norm())
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_fixed_grid_step_size_option(golden, method):
+    """options={'step_size': h} (FixedGridODESolver, solvers.py:39-99): integration on the finer grid, every requested
+    time reports the end state of the first grid step reaching it; a grid_constructor raises like the reference."""
+    import ndcn_b200 as nb
+    g = golden("ndcn_grid400")
+    OM = csr_to_dense(g, "OM")
+    W = torch.from_numpy(g["sd_neural_dynamic_layer__odefunc__wt__weight"])
+    b = torch.from_numpy(g["sd_neural_dynamic_layer__odefunc__wt__bias"])
+    h0 = torch.from_numpy(g["h0"])
+    t = torch.tensor([0.0, 0.13, 0.5, 0.51, 0.9, 1.0])
+    func = nb.ODEFunc(20, OM.cuda())
+    func.wt.weight.data.copy_(W)
+    func.wt.bias.data.copy_(b)
+    func = func.cuda().eval()
+    with torch.no_grad():
+        y = nb.odeint(func, h0.cuda(), t, method=method, options={"step_size": 0.07})
+        ref = O.odeint(lambda tt, x: O.rhs_ndcn(OM, W, b, x), h0, t, method=method, step_size=0.07)
+        yT = nb.odeint(func, h0.cuda(), t, method=method, options={"step_size": 0.07}, terminal_only=True)
+    torch.testing.assert_close(y.cpu(), ref, rtol=RTOL, atol=1e-5)
+    torch.testing.assert_close(yT, y[-1], rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        nb.odeint(func, h0.cuda(), t, method=method, options={"grid_constructor": lambda f, y0, tt: tt})
+
+
+def test_variant_forward_is_not_replaced_by_the_fused_kernel(golden):
+    """A class that merely LOOKS like the reference's ODEFunc (name + wt + A) but computes something else keeps its
+    own arithmetic: odeint fuses only forwards it knows (ours, the reference's source, explicit opt-in)."""
+    import ndcn_b200 as nb
+    from ndcn_b200.odeint import recognise
+
+    g = golden("ndcn_grid400")
+    OM = csr_to_dense(g, "OM").cuda()
+
+    class ODEFunc(torch.nn.Module):  # tanh instead of relu
+        def __init__(self, hidden, A):
+            super().__init__()
+            self.A, self.wt = A, torch.nn.Linear(hidden, hidden)
+
+        def forward(self, t, x):
+            return torch.tanh(self.wt(torch.mm(self.A, x)))
+
+    torch.manual_seed(1)
+    fn = ODEFunc(20, OM).cuda()
+    assert recognise(fn, 20, torch.device("cuda")) is None
+    x = torch.from_numpy(g["h0"]).cuda()
+    t = torch.tensor([0.0, 0.1, 0.2])
+    with torch.no_grad():
+        y = nb.odeint(fn, x, t, method="rk4")
+        ref = O.odeint(lambda tt, xx: torch.tanh(torch.nn.functional.linear(OM.cpu() @ xx, fn.wt.weight.cpu(), fn.wt.bias.cpu())),
+                       x.cpu(), t, method="rk4")
+    torch.testing.assert_close(y.cpu(), ref, rtol=RTOL, atol=1e-5)
+    # the package's own class is recognised, and so is the reference's own source (tests/test_gpu_scripts.py runs it)
+    assert recognise(nb.ODEFunc(20, OM).cuda(), 20, torch.device("cuda")) is not None

@@ -49,3 +49,37 @@ def test_irregular_grid_and_tight_tolerance():
             ref = ode.odeint(fn, x, t, method=method, **kw)
             mine = O.odeint(lambda tt, xx: O.rhs_ndcn(fn.A, fn.wt.weight, fn.wt.bias, xx), x, t, method=method, **kw)
             assert torch.equal(ref, mine), (method, kw)
+
+
+def test_fixed_grid_step_size_option_bit_exact():
+    """FixedGridODESolver's `step_size` grid and its output rule (solvers.py:39-99): every requested time reports
+    the END state of the first grid step that reaches it; a `grid_constructor` always raises."""
+    import pytest
+
+    from ndcn_b200.odeint import _fixed_grid_and_picks
+
+    nd, ode = ref_loader.import_reference()
+    torch.manual_seed(5)
+    A = (torch.rand(40, 40) < 0.15).float()
+    A = ((A + A.t()) > 0).float()
+    fn = nd.ODEFunc(8, A * 0.1)
+    x = torch.randn(40, 8)
+    t = torch.tensor([0.0, 0.13, 0.5, 0.51, 0.9, 1.0])
+    rhs = lambda tt, xx: O.rhs_ndcn(fn.A, fn.wt.weight, fn.wt.bias, xx)  # noqa: E731
+    with torch.no_grad():
+        for method in ("euler", "midpoint", "rk4"):
+            for h in (0.1, 0.07, 0.3):
+                ref = ode.odeint(fn, x, t, method=method, options={"step_size": h})
+                mine = O.odeint(rhs, x, t, method=method, step_size=h)
+                assert torch.equal(ref, mine), (method, h)
+                # the host logic of the product: same grid, same picks
+                grid, pick = _fixed_grid_and_picks(fn, x, t, h, None)
+                full = ode.odeint(fn, x, grid, method=method)
+                assert torch.equal(full[pick], ref), (method, h)
+        for opts in ({"grid_constructor": lambda f, y, tt: tt}, {"grid_constructor": lambda f, y, tt: tt, "step_size": 0.1}):
+            with pytest.raises(ValueError):
+                ode.odeint(fn, x, t, method="rk4", options=opts)
+            with pytest.raises(ValueError):
+                O.odeint(rhs, x, t, method="rk4", **opts)
+            with pytest.raises(ValueError):
+                _fixed_grid_and_picks(fn, x, t, opts.get("step_size"), opts["grid_constructor"])
