@@ -88,6 +88,11 @@ typedef struct ndcn_rhs_desc {
   float p[8];
   ndcn_rhs_callback_t callback; /* CALLBACK only */
   void* callback_user;
+  /* optional, NDCN only: the derived forms of W the kernels consume (W^T for the FP32-FMA GEMMs, the tf32 hi/lo
+   * swizzled images of W and W^T for the tcgen05 kernels), produced once by ndcn_prepare_weights_f32 and valid while
+   * W is unchanged.  NULL: ndcn_rhs_eval_f32 / ndcn_rhs_vjp_f32 derive them on every call (the solver always
+   * derives its own, once per solve).  Training loops evaluate the RHS dozens of times per optimiser step.      */
+  const void* prepared;
 } ndcn_rhs_desc_t;
 
 /* ---- graph handle ------------------------------------------------------------------
@@ -107,6 +112,11 @@ int ndcn_spmm_f32(const ndcn_graph_t* g, const float* x, float* y, int32_t H, nd
 int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x,
                       float* out, ndcn_stream_t s);
 
+/* derived weight forms for ndcn_rhs_desc_t::prepared (device buffer of ndcn_prepared_weights_bytes(H) bytes,
+ * 1024-byte aligned) */
+size_t ndcn_prepared_weights_bytes(int32_t H);
+int ndcn_prepare_weights_f32(const float* W, int32_t H, void* prepared, ndcn_stream_t s);
+
 /* vjp of one ODEFunc evaluation k = relu((Phi x) W^T + b): what autograd computes through
  * neural_dynamics.py:20-39 for the cotangent gk of k (training loops: heat_dynamics.py:333).
  *   gp = scale * gk where k > 0, else 0                 [n, H]  (dW = gp^T z, db = column sums of gp)
@@ -116,6 +126,15 @@ int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const f
 int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, const ndcn_rhs_desc_t* rhs,
                      const float* x, const float* gk, float scale, float* gx, int32_t accumulate,
                      float* gp, float* z, ndcn_stream_t s);
+
+/* Parameter gradients of the Linear inside ODEFunc from what ndcn_rhs_vjp_f32 leaves behind
+ * (autograd through nn.Linear at neural_dynamics.py:33, training loops heat_dynamics.py:333, dgnn.py:204):
+ *   dW[o][i] (+)= sum_r gp[r][o] * z[r][i]        [H, H] row-major, like nn.Linear.weight.grad
+ *   db[o]    (+)= sum_r gp[r][o]                  [H]
+ * over the n rows, summed in a fixed order (row chunks, then chunk by chunk): run-to-run reproducible.
+ * accumulate != 0 adds to dW / db, else overwrites.  db may be NULL.                                    */
+int ndcn_weight_grads_f32(const float* gp, const float* z, int64_t n, int32_t H, float* dW, float* db,
+                          int32_t accumulate, ndcn_stream_t s);
 
 /* ---- solver -------------------------------------------------------------------------- */
 enum ndcn_method { NDCN_EULER = 0, NDCN_MIDPOINT = 1, NDCN_RK4 = 2, NDCN_DOPRI5 = 3 };
@@ -196,6 +215,20 @@ int ndcn_solver_destroy(ndcn_solver_t* sv);
 int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t,
                     float* out, const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats,
                     ndcn_stream_t s);
+
+/* The same solve as ONE cooperative launch (persistent whole-solve kernel, csrc/small_solver.cuh): for problems whose
+ * every tensor stays in L2 -- BASELINE configs 1-2: the 400-node grid of the dynamics scripts (heat_dynamics.py:313-344,
+ * 99 Euler steps per model call, 2000 calls) and Cora (dgnn.py:159-237) -- where a launch per stage is nothing but
+ * launch latency.  Same arguments, same results element for element (shared device code), grid barriers where the
+ * launch boundaries were; the k_i never leave the chip's caches.  Eligible: one GPU, no callback RHS, at most 16384
+ * rows and 2^21 state elements, H <= 1024; otherwise NDCN_E_ARG.  ndcn_odeint_f32 picks it by itself when eligible
+ * (NDCN_CFG_SMALL_SOLVER = 0 switches that off); ndcn_odeint_staged_f32 always takes the launch-per-stage path.   */
+int ndcn_odeint_small_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t,
+                          float* out, const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats,
+                          ndcn_stream_t s);
+int ndcn_odeint_staged_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t,
+                           float* out, const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats,
+                           ndcn_stream_t s);
 
 /* ---- multi-GPU peer push (new; the reference is single-device) ---------------------------
  * The third exchange scheme of a 1-D row partition, and the one without a collective call on the
@@ -283,7 +316,8 @@ enum ndcn_config_key {
   NDCN_CFG_STAGE_IMPL = 0,   /* NDCN_IMPL_* */
   NDCN_CFG_GATHER_CW = 1,    /* 0 auto, -1 one pass over full rows, 16/32/64 floats per chunk */
   NDCN_CFG_UMMA_MIN_ROWS = 2,
-  NDCN_CFG_GATHER_VERSION = 3 /* chunk-major gather: 1 one row per lane group, 2 persistent CTAs + TMA-staged CSR */
+  NDCN_CFG_GATHER_VERSION = 3, /* chunk-major gather: 1 one row per lane group, 2 persistent CTAs + TMA-staged CSR */
+  NDCN_CFG_SMALL_SOLVER = 4   /* 1 (default): ndcn_odeint_f32 runs eligible solves as one persistent kernel; 0: never */
 };
 int ndcn_config_set(int32_t key, int64_t value);
 int64_t ndcn_config_get(int32_t key);

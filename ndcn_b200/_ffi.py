@@ -31,7 +31,7 @@ O_TERMINAL_ONLY, O_FORCED_DT, O_TIME_KERNELS = 1, 2, 4
 GATHER_LOCAL, GATHER_EXTERNAL = 0, 1
 K_STAGE, K_ALGEBRA, K_CONTROL, K_EMIT, K_INIT, K_GATHER, K_EXCHANGE = 0, 1, 2, 3, 4, 5, 6
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
-CFG_STAGE_IMPL, CFG_GATHER_CW, CFG_UMMA_MIN_ROWS, CFG_GATHER_VERSION = 0, 1, 2, 3
+CFG_STAGE_IMPL, CFG_GATHER_CW, CFG_UMMA_MIN_ROWS, CFG_GATHER_VERSION, CFG_SMALL_SOLVER = 0, 1, 2, 3, 4
 
 
 class RhsDesc(C.Structure):
@@ -39,6 +39,7 @@ class RhsDesc(C.Structure):
         ("kind", C.c_int32), ("flags", C.c_uint32), ("H", C.c_int32), ("reserved", C.c_int32),
         ("W", C.c_void_p), ("b", C.c_void_p), ("p", C.c_float * 8),
         ("callback", RHS_CALLBACK), ("callback_user", C.c_void_p),
+        ("prepared", C.c_void_p),
     ]
 
 
@@ -89,12 +90,20 @@ PROTOTYPES = {
     "ndcn_rhs_eval_f32": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ndcn_rhs_vjp_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RhsDesc), C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ndcn_prepared_weights_bytes": (C.c_size_t, [C.c_int32]),
+    "ndcn_prepare_weights_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ndcn_weight_grads_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p]),
     "ndcn_solver_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "ndcn_solver_create": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_int32, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_void_p)]),
     "ndcn_solver_destroy": (C.c_int, [C.c_void_p]),
     "ndcn_odeint_f32": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int32, C.c_void_p,
                                   C.POINTER(SolveOpts), C.POINTER(SolveStats), C.c_void_p]),
+    "ndcn_odeint_small_f32": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int32, C.c_void_p,
+                                        C.POINTER(SolveOpts), C.POINTER(SolveStats), C.c_void_p]),
+    "ndcn_odeint_staged_f32": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int32, C.c_void_p,
+                                         C.POINTER(SolveOpts), C.POINTER(SolveStats), C.c_void_p]),
     "ndcn_rk_combine_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), c_double_p, C.c_int32,
                                       C.c_float, C.c_int64, C.c_void_p]),
     "ndcn_error_ratio_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int64,
@@ -174,12 +183,14 @@ def check(rc: int, what: str = "ndcn call") -> None:
 
 
 def configure(stage_impl: Optional[int] = None, gather_cw: Optional[int] = None,
-              umma_min_rows: Optional[int] = None, gather_version: Optional[int] = None) -> dict:
+              umma_min_rows: Optional[int] = None, gather_version: Optional[int] = None,
+              small_solver: Optional[int] = None) -> dict:
     """Process-wide kernel-family knobs (``ndcn_config_set``); returns the previous values."""
     h = lib()
     prev = {"stage_impl": int(h.ndcn_config_get(CFG_STAGE_IMPL)), "gather_cw": int(h.ndcn_config_get(CFG_GATHER_CW)),
             "umma_min_rows": int(h.ndcn_config_get(CFG_UMMA_MIN_ROWS)),
-            "gather_version": int(h.ndcn_config_get(CFG_GATHER_VERSION))}
+            "gather_version": int(h.ndcn_config_get(CFG_GATHER_VERSION)),
+            "small_solver": int(h.ndcn_config_get(CFG_SMALL_SOLVER))}
     if stage_impl is not None:
         check(h.ndcn_config_set(CFG_STAGE_IMPL, int(stage_impl)), "ndcn_config_set")
     if gather_cw is not None:
@@ -188,4 +199,6 @@ def configure(stage_impl: Optional[int] = None, gather_cw: Optional[int] = None,
         check(h.ndcn_config_set(CFG_UMMA_MIN_ROWS, int(umma_min_rows)), "ndcn_config_set")
     if gather_version is not None:
         check(h.ndcn_config_set(CFG_GATHER_VERSION, int(gather_version)), "ndcn_config_set")
+    if small_solver is not None:
+        check(h.ndcn_config_set(CFG_SMALL_SOLVER, int(small_solver)), "ndcn_config_set")
     return prev

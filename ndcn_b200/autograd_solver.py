@@ -49,6 +49,48 @@ class SpmmFn(torch.autograd.Function):
         return _solver.spmm(ctx.graph.transpose(), g.contiguous()), None
 
 
+class RhsFn(torch.autograd.Function):
+    """One ``ODEFunc`` evaluation k = relu((Phi x) W^T + b) as a single autograd node: forward = the fused RHS kernel(s),
+    backward = ``ndcn_rhs_vjp_f32`` (gather, GEMM with ReLU-mask epilogue, GEMM with W, gather with Phi^T) plus
+    ``ndcn_weight_grads_f32`` for dW / db.  What plain autograd would record through neural_dynamics.py:27-36 as
+    sparse.mm + addmm + relu (3 forward, ~6 backward launches, z and the pre-activation kept alive); here only x
+    is saved and z / the mask are recomputed."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, graph, graph_t, flags):
+        from . import _ffi
+
+        no_control = bool(flags & _ffi.F_NO_CONTROL)
+        spec = _solver.RhsSpec(_ffi.RHS_NDCN, int(x.shape[1]), flags, None if no_control else W, None if no_control else b)
+        ctx.save_for_backward(x, W, b)
+        ctx.graph, ctx.graph_t, ctx.flags = graph, graph_t, flags
+        return _solver.rhs_eval(graph, spec, x.contiguous())
+
+    @staticmethod
+    def backward(ctx, gk):
+        from . import _ffi
+
+        x, W, b = ctx.saved_tensors
+        flags = ctx.flags
+        no_control = bool(flags & _ffi.F_NO_CONTROL)
+        spec = _solver.RhsSpec(_ffi.RHS_NDCN, int(x.shape[1]), flags, None if no_control else W, None if no_control else b)
+        x = x.contiguous()
+        gx = torch.empty_like(x)
+        gp, z = _vjp(ctx.graph, ctx.graph_t, spec, x, gk.contiguous(), 1.0, gx, False)
+        dW = db = None
+        if not no_control:
+            need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+            if need_w or need_b:
+                dW = torch.empty_like(W)
+                db = torch.empty_like(b)
+                _solver.weight_grads(gp, z, dW, db, accumulate=False)
+                if not need_w:
+                    dW = None
+                if not need_b:
+                    db = None
+        return (gx if ctx.needs_input_grad[0] else None), dW, db, None, None, None
+
+
 def _require_cuda_state(y0: torch.Tensor) -> None:
     if not y0.is_cuda:
         raise RuntimeError(
@@ -208,7 +250,7 @@ def _vjp(graph: CsrGraph, graph_t: CsrGraph, spec, x, gk, scale: float, gx, accu
     gp = torch.empty_like(x)
     z = torch.empty_like(x) if not (spec.flags & _ffi.F_NO_GRAPH) else x
     keep: list = []
-    desc = spec.to_c(keep)
+    desc = spec.to_c(keep, prepare=True)
     with torch.cuda.device(x.device):
         rc = _ffi.lib().ndcn_rhs_vjp_f32(graph.handle, graph_t.handle, C.byref(desc), x.data_ptr(), gk.data_ptr(),
                                          float(scale), gx.data_ptr(), 1 if accumulate else 0, gp.data_ptr(),
@@ -255,8 +297,7 @@ class FusedFixedGridFn(torch.autograd.Function):
         def vjp(x, gk, scale, gx, accumulate=True):
             gp, z = _vjp(graph, graph_t, spec, x, gk, scale, gx, accumulate)
             if not no_control:
-                dW.addmm_(gp.t(), z)
-                db.add_(gp.sum(0))
+                _solver.weight_grads(gp, z, dW, db, accumulate=True)  # dW += gp^T z, db += sum_r gp
 
         for i in range(slab.shape[0] - 2, -1, -1):
             y = slab[i]

@@ -20,6 +20,7 @@
 #include "stage_kernels.cuh"
 #include "gather_kernels.cuh"
 #include "umma_kernels.cuh"
+#include "small_solver.cuh"
 
 using namespace ndcn;
 
@@ -49,6 +50,9 @@ struct Config {
   int gather_cw = 0;                // 0 auto, -1 full-row gather, else chunk width in floats (16/32/64)
   int64_t umma_min_rows = 8192;     // auto: tcgen05 path from this many rows
   int gather_v = 1;                 // chunk-major gather flavour: 1 one row per lane group, 2 persistent + TMA-staged CSR
+  int small_solver = 1;             // 1: solves that fit the persistent whole-solve kernel use it (ndcn_odeint_f32 auto)
+  int64_t small_max_rows = 16384;   // ... up to this many rows
+  int64_t small_max_numel = 1 << 21;  // ... and this many state elements (8 MB per buffer: everything stays in L2)
 };
 static Config& cfg() {
   static Config c = [] {
@@ -57,6 +61,7 @@ static Config& cfg() {
     if (const char* v = std::getenv("NDCN_GATHER_CW")) k.gather_cw = std::atoi(v);
     if (const char* v = std::getenv("NDCN_UMMA_MIN_ROWS")) k.umma_min_rows = std::atoll(v);
     if (const char* v = std::getenv("NDCN_GATHER_V")) k.gather_v = std::atoi(v);
+    if (const char* v = std::getenv("NDCN_SMALL_SOLVER")) k.small_solver = std::atoi(v) != 0;
     return k;
   }();
   return c;
@@ -80,6 +85,10 @@ extern "C" int ndcn_config_set(int32_t key, int64_t value) {
       if (value != 1 && value != 2) return NDCN_E_ARG;
       cfg().gather_v = (int)value;
       return NDCN_OK;
+    case NDCN_CFG_SMALL_SOLVER:
+      if (value != 0 && value != 1) return NDCN_E_ARG;
+      cfg().small_solver = (int)value;
+      return NDCN_OK;
     default:
       return NDCN_E_ARG;
   }
@@ -91,6 +100,7 @@ extern "C" int64_t ndcn_config_get(int32_t key) {
     case NDCN_CFG_GATHER_CW: return cfg().gather_cw;
     case NDCN_CFG_UMMA_MIN_ROWS: return cfg().umma_min_rows;
     case NDCN_CFG_GATHER_VERSION: return cfg().gather_v;
+    case NDCN_CFG_SMALL_SOLVER: return cfg().small_solver;
     default: return NDCN_E_ARG;
   }
 }
@@ -134,14 +144,17 @@ static int sm_count_now() {
   return cached[dev];
 }
 // cudaFuncSetAttribute is per device: remember it per (kernel instantiation, device)
+// (marked only AFTER the call has returned: ranks that run as threads of one process may race here, and a
+// duplicate cudaFuncSetAttribute is harmless while a launch that overtakes the first one is not)
 struct PerDeviceOnce {
-  bool done[64] = {};
-  bool need() {
+  volatile bool done[64] = {};
+  bool need() const {
     const int dev = current_device();
-    if (dev < 0 || dev >= 64) return true;
-    if (done[dev]) return false;
-    done[dev] = true;
-    return true;
+    return dev < 0 || dev >= 64 || !done[dev];
+  }
+  void mark() {
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64) done[dev] = true;
   }
 };
 
@@ -246,9 +259,11 @@ static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaSt
   } else {
     using S = GemmSmem<VW, NCH>;
     static PerDeviceOnce attr;
-    if (attr.need())
+    if (attr.need()) {
       CU_TRY(cudaFuncSetAttribute(k_stage_ndcn_gemm<VW, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)S::total));
+      attr.mark();
+    }
     const int grid = (int)((n + kTileRows - 1) / kTileRows);
     *grid_out = grid;
     k_stage_ndcn_gemm<VW, NCH><<<grid, kStageThreads, S::total, st>>>(a, e);
@@ -390,9 +405,11 @@ template <int H, int MODE, int NPREV, int B>
 static int launch_umma_inst(const UmmaArgs& u, EpiArgs& e, int grid, cudaStream_t st) {
   using Cf = UmmaCfg<H>;
   static PerDeviceOnce attr;
-  if (attr.need())
+  if (attr.need()) {
     CU_TRY(cudaFuncSetAttribute(k_stage_gemm_umma<H, MODE, NPREV, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)Cf::kSmemBytes));
+    attr.mark();
+  }
   k_stage_gemm_umma<H, MODE, NPREV, B><<<grid, kUmmaThreads, Cf::kSmemBytes, st>>>(u, e);
   return (int)cudaGetLastError();
 }
@@ -672,6 +689,81 @@ static void prep_w_image(const float* W, float* img, cudaStream_t st) {
   k_prep_w_image<H><<<(H * H + 255) / 256, 256, 0, st>>>(W, img);
 }
 
+// layout of ndcn_rhs_desc_t::prepared
+struct PreparedView {
+  const float* Wt = nullptr;       // [H,H] = W^T
+  const float* img_fwd = nullptr;  // tf32 hi/lo image of W    (H in {128, 256})
+  const float* img_bwd = nullptr;  // tf32 hi/lo image of W^T  (H in {128, 256})
+  const float* zeros = nullptr;    // [H]
+};
+static size_t prepared_off_img(int H) { return align_up(sizeof(float) * (size_t)H * H, 1024); }
+static size_t prepared_img_bytes(int H) { return (H == 256 || H == 128) ? align_up(sizeof(float) * 2 * (size_t)H * H, 1024) : 0; }
+static PreparedView prepared_view(const void* p, int H) {
+  PreparedView v;
+  if (!p) return v;
+  const unsigned char* b = (const unsigned char*)p;
+  v.Wt = (const float*)b;
+  const size_t img = prepared_img_bytes(H);
+  if (img) {
+    v.img_fwd = (const float*)(b + prepared_off_img(H));
+    v.img_bwd = (const float*)(b + prepared_off_img(H) + img);
+  }
+  v.zeros = (const float*)(b + prepared_off_img(H) + 2 * img);
+  return v;
+}
+
+extern "C" size_t ndcn_prepared_weights_bytes(int32_t H) {
+  if (H < 1) return 0;
+  return prepared_off_img(H) + 2 * prepared_img_bytes(H) + align_up(sizeof(float) * (size_t)H, 1024);
+}
+
+extern "C" int ndcn_prepare_weights_f32(const float* W, int32_t H, void* prepared, ndcn_stream_t s) {
+  if (!W || !prepared || H < 1 || H > 1024 || ((uintptr_t)prepared & 1023u)) return NDCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)s;
+  PreparedView v = prepared_view(prepared, H);
+  float* Wt = const_cast<float*>(v.Wt);
+  k_transpose<<<(H * H + 255) / 256, 256, 0, st>>>(W, Wt, H);
+  CU_TRY(cudaMemsetAsync(const_cast<float*>(v.zeros), 0, sizeof(float) * H, st));
+  if (H == 256) {
+    prep_w_image<256>(W, const_cast<float*>(v.img_fwd), st);
+    prep_w_image<256>(Wt, const_cast<float*>(v.img_bwd), st);
+  } else if (H == 128) {
+    prep_w_image<128>(W, const_cast<float*>(v.img_fwd), st);
+    prep_w_image<128>(Wt, const_cast<float*>(v.img_bwd), st);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ndcn_weight_grads_f32(const float* gp, const float* z, int64_t n, int32_t H, float* dW, float* db,
+                                     int32_t accumulate, ndcn_stream_t s) {
+  if (!gp || !z || !dW || n < 0 || H < 1 || H > 1024) return NDCN_E_ARG;
+  cudaStream_t st = (cudaStream_t)s;
+  keep_scratch_pooled();
+  const int64_t hh = (int64_t)H * H;
+  if (n == 0) {
+    if (!accumulate) {
+      CU_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * hh, st));
+      if (db) CU_TRY(cudaMemsetAsync(db, 0, sizeof(float) * H, st));
+    }
+    return NDCN_OK;
+  }
+  const int tiles = (H + kWgTile - 1) / kWgTile;
+  // enough row chunks to fill the chip twice, at least 64 rows each
+  int64_t nz = std::max<int64_t>(1, (2 * (int64_t)sm_count_now() + tiles * tiles - 1) / (tiles * tiles));
+  nz = std::min<int64_t>(nz, (n + 63) / 64);
+  int64_t rows_per_chunk = (n + nz - 1) / nz;
+  rows_per_chunk = (rows_per_chunk + kWgK - 1) / kWgK * kWgK;
+  nz = (n + rows_per_chunk - 1) / rows_per_chunk;
+  float* part = nullptr;
+  CU_TRY(cudaMallocAsync((void**)&part, sizeof(float) * (size_t)nz * (hh + H), st));
+  float* part_b = db ? part + (size_t)nz * hh : nullptr;
+  k_weight_grads_partial<<<dim3(tiles, tiles, (unsigned)nz), 256, 0, st>>>(gp, z, n, H, rows_per_chunk, part, part_b);
+  k_weight_grads_reduce<<<(unsigned)((hh + 255) / 256), 256, 0, st>>>(part, (int)nz, hh, dW, accumulate ? 1 : 0);
+  if (db) k_weight_grads_reduce<<<(H + 255) / 256, 256, 0, st>>>(part_b, (int)nz, H, db, accumulate ? 1 : 0);
+  cudaFreeAsync(part, st);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* rhs, const float* x, float* out,
                                  ndcn_stream_t s) {
   if (!g || !rhs || !x || !out) return NDCN_E_ARG;
@@ -685,22 +777,29 @@ extern "C" int ndcn_rhs_eval_f32(const ndcn_graph_t* g, const ndcn_rhs_desc_t* r
   if (need_wt || use_umma) {
     if (!rhs->W) return NDCN_E_ARG;
   }
-  if (need_wt) {
+  const PreparedView pv = prepared_view(rhs->kind == NDCN_RHS_NDCN ? rhs->prepared : nullptr, rhs->H);
+  const float* Wt_use = pv.Wt;
+  const float* Wimg_use = pv.img_fwd;
+  if (need_wt && !Wt_use) {
     CU_TRY(cudaMallocAsync((void**)&Wt, sizeof(float) * rhs->H * rhs->H, st));
     const int n = rhs->H * rhs->H;
     k_transpose<<<(n + 255) / 256, 256, 0, st>>>(rhs->W, Wt, rhs->H);
+    Wt_use = Wt;
   }
   if (use_umma) {
-    CU_TRY(cudaMallocAsync((void**)&Wimg, sizeof(float) * 2 * rhs->H * rhs->H, st));
     if (!(rhs->flags & NDCN_F_NO_GRAPH))
       CU_TRY(cudaMallocAsync((void**)&Z, sizeof(float) * (size_t)g->v.n_rows * rhs->H, st));
-    if (rhs->H == 256) prep_w_image<256>(rhs->W, Wimg, st);
-    else prep_w_image<128>(rhs->W, Wimg, st);
+    if (!Wimg_use) {
+      CU_TRY(cudaMallocAsync((void**)&Wimg, sizeof(float) * 2 * rhs->H * rhs->H, st));
+      if (rhs->H == 256) prep_w_image<256>(rhs->W, Wimg, st);
+      else prep_w_image<128>(rhs->W, Wimg, st);
+      Wimg_use = Wimg;
+    }
   }
-  RhsBinding b{g, rhs, Wt, nullptr, 0, sm_count_now()};
+  RhsBinding b{g, rhs, Wt_use, nullptr, 0, sm_count_now()};
   // without Z the dispatcher falls back to the SIMT kernels; no_graph needs no Z: give it a non-null tag
   b.Z = use_umma ? (Z ? Z : out) : nullptr;
-  b.Wimg = Wimg;
+  b.Wimg = Wimg_use;
   int rc = launch_stage(b, pp(const_cast<float*>(x)), store_only(out), nullptr, st);
   if (Wt) cudaFreeAsync(Wt, st);
   if (Z) cudaFreeAsync(Z, st);
@@ -763,29 +862,39 @@ extern "C" int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, 
     RC_TRY(elementwise(zin, em));
   } else {
     const bool use_umma = umma_eligible(*rhs, n) && vec;
-    const size_t img = use_umma ? align_up(sizeof(float) * 2 * (size_t)H * H, 1024) : 0;
-    const size_t bytes = align_up(sizeof(float) * (size_t)numel, 1024) + align_up(sizeof(float) * (size_t)H * H, 1024) +
-                         align_up(sizeof(float) * (size_t)H, 1024) + 2 * img + 1024;
+    const PreparedView pv = prepared_view(rhs->prepared, H);
+    const bool have_prep = pv.Wt != nullptr && (!use_umma || pv.img_fwd != nullptr);
+    const size_t img = (use_umma && !have_prep) ? align_up(sizeof(float) * 2 * (size_t)H * H, 1024) : 0;
+    const size_t bytes = align_up(sizeof(float) * (size_t)numel, 1024) +
+                         (have_prep ? 0 : align_up(sizeof(float) * (size_t)H * H, 1024) + align_up(sizeof(float) * (size_t)H, 1024)) +
+                         2 * img + 1024;
     CU_TRY(cudaMallocAsync((void**)&scratch, bytes, st));
     unsigned char* p = (unsigned char*)align_up((size_t)scratch, 1024);
     u = (float*)p;
     p += align_up(sizeof(float) * (size_t)numel, 1024);
-    float* Wt = (float*)p;
-    p += align_up(sizeof(float) * (size_t)H * H, 1024);
-    float* zeros = (float*)p;
-    p += align_up(sizeof(float) * (size_t)H, 1024);
-    float* img_fwd = use_umma ? (float*)p : nullptr;
-    float* img_bwd = use_umma ? (float*)(p + img) : nullptr;
-    k_transpose<<<(H * H + 255) / 256, 256, 0, st>>>(rhs->W, Wt, H);
-    CU_TRY(cudaMemsetAsync(zeros, 0, sizeof(float) * H, st));
-    if (use_umma) {
-      if (H == 256) {
-        prep_w_image<256>(rhs->W, img_fwd, st);
-        prep_w_image<256>(Wt, img_bwd, st);
-      } else {
-        prep_w_image<128>(rhs->W, img_fwd, st);
-        prep_w_image<128>(Wt, img_bwd, st);
+    const float* Wt = pv.Wt;
+    const float* zeros = pv.zeros;
+    const float* img_fwd = use_umma ? pv.img_fwd : nullptr;
+    const float* img_bwd = use_umma ? pv.img_bwd : nullptr;
+    if (!have_prep) {
+      float* Wt_w = (float*)p;
+      p += align_up(sizeof(float) * (size_t)H * H, 1024);
+      float* zeros_w = (float*)p;
+      p += align_up(sizeof(float) * (size_t)H, 1024);
+      float* img_fwd_w = use_umma ? (float*)p : nullptr;
+      float* img_bwd_w = use_umma ? (float*)(p + img) : nullptr;
+      k_transpose<<<(H * H + 255) / 256, 256, 0, st>>>(rhs->W, Wt_w, H);
+      CU_TRY(cudaMemsetAsync(zeros_w, 0, sizeof(float) * H, st));
+      if (use_umma) {
+        if (H == 256) {
+          prep_w_image<256>(rhs->W, img_fwd_w, st);
+          prep_w_image<256>(Wt_w, img_bwd_w, st);
+        } else {
+          prep_w_image<128>(rhs->W, img_fwd_w, st);
+          prep_w_image<128>(Wt_w, img_bwd_w, st);
+        }
       }
+      Wt = Wt_w; zeros = zeros_w; img_fwd = img_fwd_w; img_bwd = img_bwd_w;
     }
     // pre-activation mask: the forward GEMM on z with the mask epilogue
     ndcn_rhs_desc_t rf = *rhs;
@@ -1207,6 +1316,31 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
   return 0;
 }
 
+// controller block at the start of a dopri5 solve (single-GPU element count; the multi-GPU drivers overwrite it)
+static void fill_ctrl(Ctrl& h, const Driver& d, const double* t, int n_t) {
+  const ndcn_solve_opts_t* o = d.o;
+  const bool forced = (o->flags & NDCN_O_FORCED_DT) != 0;
+  std::memset(&h, 0, sizeof(h));
+  h.t0 = h.t1 = t[0];
+  h.rtol = o->rtol;
+  h.atol = o->atol;
+  // _convert_to_tensor(0.9, float64) goes through an fp32 tensor first (misc.py:39-47)
+  h.safety = (double)(float)(o->safety > 0 ? o->safety : 0.9);
+  h.ifactor = (double)(float)(o->ifactor > 0 ? o->ifactor : 10.0);
+  h.dfactor = (double)(float)(o->dfactor > 0 ? o->dfactor : 0.2);
+  h.forced = forced ? 1 : 0;
+  h.forced_dt = o->forced_dt;
+  const bool given_first = !forced && o->first_step > 0.0;
+  h.dt = forced ? o->forced_dt : (given_first ? o->first_step : 0.0);
+  h.first_step = h.dt;
+  h.numel_global = (double)d.sv->numel;
+  h.max_num_steps = o->max_num_steps > 0 ? o->max_num_steps : 2147483647LL;
+  h.next_out = 1;
+  h.n_out = n_t;
+  h.emit_lo = h.emit_hi = 1;
+  h.terminal_only = (o->flags & NDCN_O_TERMINAL_ONLY) ? 1 : 0;
+}
+
 // ---- dopri5 ------------------------------------------------------------------------------
 struct Dopri {
   Driver& d;
@@ -1341,25 +1475,8 @@ struct Dopri {
     CU_TRY(cudaMemcpyAsync(sv->t_out, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
 
     Ctrl& h = *sv->ctrl_host;
-    std::memset(&h, 0, sizeof(h));
-    h.t0 = h.t1 = t[0];
-    h.rtol = d.o->rtol;
-    h.atol = d.o->atol;
-    // _convert_to_tensor(0.9, float64) goes through an fp32 tensor first (misc.py:39-47)
-    h.safety = (double)(float)(d.o->safety > 0 ? d.o->safety : 0.9);
-    h.ifactor = (double)(float)(d.o->ifactor > 0 ? d.o->ifactor : 10.0);
-    h.dfactor = (double)(float)(d.o->dfactor > 0 ? d.o->dfactor : 0.2);
-    h.forced = forced ? 1 : 0;
-    h.forced_dt = d.o->forced_dt;
+    fill_ctrl(h, d, t, n_t);
     const bool given_first = !forced && d.o->first_step > 0.0;
-    h.dt = forced ? d.o->forced_dt : (given_first ? d.o->first_step : 0.0);
-    h.first_step = h.dt;
-    h.numel_global = (double)sv->numel;  // multi-GPU: overwritten below through the hook
-    h.max_num_steps = d.o->max_num_steps > 0 ? d.o->max_num_steps : 2147483647LL;
-    h.next_out = 1;
-    h.n_out = n_t;
-    h.emit_lo = h.emit_hi = 1;
-    h.terminal_only = terminal ? 1 : 0;
     if (d.feat()) {
       h.numel_global = (double)sv->feat_bounds[sv->feat_world] * (double)sv->H;
     } else if (d.push()) {
@@ -1456,10 +1573,149 @@ struct Dopri {
   }
 };
 
+
+// ---- persistent whole-solve kernel (small graphs) ---------------------------------------------------------
+static bool small_eligible(const ndcn_solver* sv, const ndcn_solve_opts_t* o) {
+  if (sv->n_push > 0 || sv->feat_on || o->exchange != nullptr || o->gather_mode != NDCN_GATHER_LOCAL) return false;
+  if (sv->n_cols != sv->n_rows || sv->rhs.kind == NDCN_RHS_CALLBACK) return false;
+  if (sv->H < 1 || sv->H > 1024 || sv->n_rows < 1) return false;
+  if (sv->n_rows > cfg().small_max_rows || sv->numel > cfg().small_max_numel) return false;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, current_device()) != cudaSuccess || !coop) return false;
+  return true;
+}
+
+template <int VW, int NCH, bool CONTROL>
+static int launch_small(const SmallArgs& a, size_t smem, int sm_count, int want_blocks, int* grid_out, cudaStream_t st) {
+  static PerDeviceOnce attr;
+  if (attr.need() && smem > 48 * 1024) {
+    CU_TRY(cudaFuncSetAttribute(k_solve_small<VW, NCH, CONTROL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr.mark();
+  }
+  int per_sm = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_small<VW, NCH, CONTROL>, kStageThreads, smem));
+  if (per_sm < 1) return NDCN_E_ARG;
+  // all CTAs must be co-resident (grid barriers); more CTAs than the work needs only make the barriers dearer
+  const int grid = std::max(1, std::min(want_blocks, per_sm * sm_count));
+  *grid_out = grid;
+  SmallArgs copy = a;
+  void* params[] = {&copy};
+  return (int)cudaLaunchCooperativeKernel((void*)k_solve_small<VW, NCH, CONTROL>, dim3(grid), dim3(kStageThreads), params,
+                                          smem, st);
+}
+
+static int run_small(Driver& d, const float* y0, const double* t, int n_t, float* out) {
+  ndcn_solver* sv = d.sv;
+  cudaStream_t st = d.st;
+  const ndcn_solve_opts_t* o = d.o;
+  const bool terminal = (o->flags & NDCN_O_TERMINAL_ONLY) != 0;
+  const bool forced = (o->flags & NDCN_O_FORCED_DT) != 0;
+  SmallArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.g = sv->g->v;
+  a.kind = sv->rhs.kind;
+  a.H = sv->H;
+  a.flags = sv->rhs.flags;
+  a.W = sv->rhs.W;
+  a.Wt = sv->Wt;
+  a.bias = sv->rhs.b;
+  for (int i = 0; i < 8; ++i) a.p[i] = sv->rhs.p[i];
+  a.method = sv->method;
+  a.n_t = n_t;
+  a.terminal = terminal ? 1 : 0;
+  a.forced = forced ? 1 : 0;
+  a.given_first = (!forced && o->first_step > 0.0) ? 1 : 0;
+  a.in_slab = (sv->method != NDCN_DOPRI5 && !terminal && !d.decoding()) ? 1 : 0;
+  a.y0 = y0;
+  a.out = out;
+  for (int i = 0; i < 2; ++i) { a.Y[i] = sv->Y[i]; a.YS[i] = sv->YS[i]; a.KF[i] = sv->KF[i]; }
+  for (int i = 0; i < 5; ++i) a.K[i] = sv->K[i];
+  a.ctrl = sv->ctrl;
+  a.partials = sv->partials;
+  for (int s = 0; s < 6; ++s)
+    for (int j = 0; j <= s; ++j) a.beta32[s][j] = (float)kDpBeta[s][j];
+  for (int j = 0; j < 7; ++j) { a.err32[j] = (float)kDpErr[j]; a.c_mid[j] = (float)kDpMid[j]; }
+  a.rtol = (float)o->rtol;
+  a.atol = (float)o->atol;
+  a.t_first = t[0];
+  a.dec_W = d.decoding() ? o->dec_W : nullptr;
+  a.dec_b = d.decoding() ? o->dec_b : nullptr;
+  a.dec_C = d.decoding() ? o->dec_classes : 0;
+  a.numel = sv->numel;
+  a.n_rows = (int)sv->n_rows;
+  a.vec = d.vec_ok ? 1 : 0;
+  a.err_prefix = 1;
+  if (const char* v = std::getenv("NDCN_ERR_PREFIX")) a.err_prefix = std::atoi(v) != 0;
+  if (sv->rhs.kind == NDCN_RHS_NDCN && !(sv->rhs.flags & NDCN_F_NO_CONTROL) && (!sv->rhs.W || !sv->rhs.b)) return NDCN_E_ARG;
+
+  // requested times (dopri5, float64) or step sizes (fixed grid, fp32) -> the solver's device scratch
+  if (sv->t_cap < n_t) {
+    if (sv->t_out) cudaFree(sv->t_out);
+    sv->t_cap = std::max(n_t, 128);
+    CU_TRY(cudaMalloc((void**)&sv->t_out, sizeof(double) * sv->t_cap));
+  }
+  std::vector<float> dts;
+  if (sv->method == NDCN_DOPRI5) {
+    CU_TRY(cudaMemcpyAsync(sv->t_out, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
+    a.t_out = sv->t_out;
+    Ctrl& h = *sv->ctrl_host;
+    fill_ctrl(h, d, t, n_t);
+    CU_TRY(cudaMemcpyAsync(sv->ctrl, &h, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));  // ctrl_host is the read-back target below; `t` may be a temporary
+  } else {
+    dts.resize(std::max(1, n_t - 1));
+    for (int i = 0; i + 1 < n_t; ++i) dts[i] = (float)t[i + 1] - (float)t[i];  // solvers.py:81,89: fp32 grid, fp32 difference
+    CU_TRY(cudaMemcpyAsync(sv->t_out, dts.data(), sizeof(float) * dts.size(), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    a.dts = reinterpret_cast<const float*>(sv->t_out);
+  }
+
+  const bool wide = sv->rhs.kind == NDCN_RHS_NDCN && fast_width(sv->H) && sv->H > 32 && aligned16(y0) && aligned16(out);
+  const bool tiled = wide && !(sv->rhs.flags & NDCN_F_NO_CONTROL);
+  const bool rowvec = wide && (sv->rhs.flags & NDCN_F_NO_CONTROL);
+  const int by_rows = (int)((sv->n_rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  const int by_tiles = (int)((sv->n_rows + kTileRows - 1) / kTileRows);
+  const int by_elems = (int)((sv->numel + kStageThreads * 4 - 1) / (kStageThreads * 4));
+  const int want = std::max(tiled ? by_tiles : std::min(by_rows, 4 * sv->sm_count), std::min(by_elems, sv->sm_count));
+  int grid = 0, rc = 0;
+  sv->launches += 1;
+  d.t_begin(NDCN_K_STAGE);
+  if (tiled) {
+    switch (sv->H) {
+      case 256: rc = launch_small<4, 2, true>(a, GemmSmem<4, 2>::total, sv->sm_count, want, &grid, st); break;
+      case 128: rc = launch_small<4, 1, true>(a, GemmSmem<4, 1>::total, sv->sm_count, want, &grid, st); break;
+      default: rc = launch_small<2, 1, true>(a, GemmSmem<2, 1>::total, sv->sm_count, want, &grid, st); break;
+    }
+  } else if (rowvec) {
+    switch (sv->H) {
+      case 256: rc = launch_small<4, 2, false>(a, 128, sv->sm_count, want, &grid, st); break;
+      case 128: rc = launch_small<4, 1, false>(a, 128, sv->sm_count, want, &grid, st); break;
+      default: rc = launch_small<2, 1, false>(a, 128, sv->sm_count, want, &grid, st); break;
+    }
+  } else {
+    rc = launch_small<0, 0, false>(a, sizeof(float) * kWarpsPerCta * std::max(sv->H, 32), sv->sm_count, want, &grid, st);
+  }
+  d.t_end();
+  if (rc != 0) return rc;
+  if (2 * grid > 2 * sv->max_partials) return NDCN_E_WORKSPACE;
+  if (sv->method == NDCN_DOPRI5) {
+    RC_TRY(d.poll());
+  } else {
+    CU_TRY(cudaStreamSynchronize(st));
+    sv->ctrl_host->n_accept = n_t - 1;
+    sv->ctrl_host->t1 = t[n_t - 1];
+    const int per_step = sv->method == NDCN_EULER ? 1 : (sv->method == NDCN_MIDPOINT ? 2 : 4);
+    d.nfe = (int64_t)per_step * (n_t - 1);
+  }
+  return 0;
+}
+
 }  // namespace
 
-extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t, float* out,
-                               const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats, ndcn_stream_t s) {
+// small_mode: 0 = the persistent whole-solve kernel when the problem is eligible and the configuration allows it,
+//             1 = require it (ndcn_odeint_small_f32), -1 = never
+static int odeint_impl(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t, float* out,
+                       const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats, ndcn_stream_t s, int small_mode) {
   if (!sv || !y0 || !t_host || !out || !opts || n_t < 1) return NDCN_E_ARG;
   if (opts->method != sv->method) return NDCN_E_METHOD;
   for (int i = 0; i + 1 < n_t; ++i)
@@ -1473,6 +1729,11 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   if (stats) std::memset(stats, 0, sizeof(*stats));
   std::memset(sv->ctrl_host, 0, sizeof(Ctrl));
 
+  const bool small_ok = small_eligible(sv, opts);
+  if (small_mode == 1 && !small_ok) return NDCN_E_ARG;
+  // auto: only where the launch-per-stage path would not run its tcgen05 kernels anyway
+  const bool use_small = n_t > 1 && small_ok &&
+                         (small_mode == 1 || (small_mode == 0 && cfg().small_solver && !umma_eligible(sv->rhs, sv->n_rows)));
   const bool fast_h = sv->H == 256 || sv->H == 128 || sv->H == 64 || sv->H == 32;
   if (sv->rhs.kind == NDCN_RHS_NDCN && !(sv->rhs.flags & NDCN_F_NO_CONTROL) && fast_h) {
     const int n = sv->H * sv->H;
@@ -1485,7 +1746,7 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   const bool external = opts->gather_mode == NDCN_GATHER_EXTERNAL || sv->feat_on;
   if (sv->feat_on && (opts->gather_mode != NDCN_GATHER_LOCAL || opts->exchange)) return NDCN_E_ARG;
   if (external && !(umma_eligible(sv->rhs, ((int64_t)1) << 40) && sv->Wimg && sv->Z)) return NDCN_E_ARG;
-  if ((external || umma_eligible(sv->rhs, sv->n_rows)) && sv->Wimg) {
+  if (!use_small && (external || umma_eligible(sv->rhs, sv->n_rows)) && sv->Wimg) {
     if (sv->H == 256) prep_w_image<256>(sv->rhs.W, sv->Wimg, st);
     else prep_w_image<128>(sv->rhs.W, sv->Wimg, st);
     sv->launches += 1;
@@ -1495,6 +1756,8 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   if (n_t == 1) {
     rc = d.put_state(out, 0, y0);
     if (!rc) rc = (int)cudaStreamSynchronize(st);
+  } else if (use_small) {
+    rc = run_small(d, y0, t_host, n_t, out);
   } else if (sv->method == NDCN_DOPRI5) {
     Dopri dp(d);
     rc = dp.run(y0, t_host, n_t, out);
@@ -1532,6 +1795,21 @@ extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double*
   }
   if (rc != 0) return rc;
   return sv->ctrl_host->status;
+}
+
+extern "C" int ndcn_odeint_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t, float* out,
+                               const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats, ndcn_stream_t s) {
+  return odeint_impl(sv, y0, t_host, n_t, out, opts, stats, s, 0);
+}
+
+extern "C" int ndcn_odeint_small_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t, float* out,
+                                     const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats, ndcn_stream_t s) {
+  return odeint_impl(sv, y0, t_host, n_t, out, opts, stats, s, 1);
+}
+
+extern "C" int ndcn_odeint_staged_f32(ndcn_solver_t* sv, const float* y0, const double* t_host, int32_t n_t, float* out,
+                                      const ndcn_solve_opts_t* opts, ndcn_solve_stats_t* stats, ndcn_stream_t s) {
+  return odeint_impl(sv, y0, t_host, n_t, out, opts, stats, s, -1);
 }
 
 // ---------------------------------------------------------------------------------------

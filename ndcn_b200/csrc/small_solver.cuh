@@ -1,0 +1,505 @@
+// Persistent whole-solve kernel for small graphs (SURVEY.md section 7.1-7, section 8(b) ndcn_odeint_small_f32).
+//
+// BASELINE configs 1-2 integrate a few hundred to a few thousand nodes (400-node grid, H=20, 99 Euler steps;
+// Cora, 2708 nodes, H=256, dopri5): every tensor of the solve fits L2 many times over and a launch-per-stage
+// schedule is nothing but launch latency (round 1: 63 launches for a 3-step dopri5 solve on 400 nodes).  Here ONE
+// cooperative launch runs the whole odeint(): the same right-hand-side row code, stage epilogues, controller
+// arithmetic and dense output as the launch-per-stage path (the device functions are shared, so the two paths
+// round identically per element), with cooperative-groups grid barriers where the launch boundaries were.  The k_i,
+// the stage inputs and the state never leave L2 -- on these sizes the north star's "no intermediate k_i hits HBM"
+// holds literally.
+//
+// Reference: torchdiffeq/_impl/solvers.py:25-33,79-99 (drivers), dopri5.py:58-122, rk_common.py:22-78,
+// fixed_grid.py:5-29, misc.py:84-170, interp.py:5-65; right-hand sides neural_dynamics.py:20-39 and the three
+// ground-truth dynamics.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "ndcn_common.cuh"
+#include "solver_kernels.cuh"
+#include "stage_kernels.cuh"
+
+namespace ndcn {
+
+namespace cg = cooperative_groups;
+
+struct SmallArgs {
+  // right-hand side
+  GraphView g;
+  int kind;          // NDCN_RHS_*
+  int H;             // state width
+  uint32_t flags;    // NDCN_F_*
+  const float* W;    // [H,H] nn.Linear weight (row-major, y = x W^T + b)
+  const float* Wt;   // [H,H] its transpose (tiled-GEMM instantiations: H in {32,64,128,256} with the Linear)
+  const float* bias;
+  float p[8];
+  // solve
+  int method;        // NDCN_EULER .. NDCN_DOPRI5
+  int n_t;
+  int terminal, forced, given_first;
+  int in_slab;       // fixed grid: the output slab doubles as state storage
+  const float* y0;
+  float* out;
+  float* Y[2];
+  float* YS[2];
+  float* KF[2];
+  float* K[5];
+  const float* dts;      // fixed grid: n_t - 1 fp32 step sizes (fp32 differences of the fp32-rounded grid)
+  const double* t_out;   // dopri5: requested times, device
+  Ctrl* ctrl;
+  double* partials;      // >= 2 * gridDim.x doubles
+  float beta32[6][8];
+  float err32[8];
+  float c_mid[7];
+  float rtol, atol;
+  double t_first;
+  const float* dec_W;    // fused decoder (NDCN.output_layer) or null
+  const float* dec_b;
+  int dec_C;
+  int64_t numel;
+  int n_rows;
+  int vec;               // elementwise phases may use 16-byte accesses
+  int err_prefix;        // stage 5 leaves the error-estimate prefix in YS[1]
+};
+
+__device__ __forceinline__ PtrPair spp(float* a) { return PtrPair{{a, a}}; }
+__device__ __forceinline__ PtrPair spp(float* a, float* b) { return PtrPair{{a, b}}; }
+
+__device__ __forceinline__ void small_blank(EpiArgs& e) {
+  // EpiArgs has no constructor (it travels as a kernel parameter): clear it field-wise
+  e.mode = EPI_STORE; e.n_prev = 0; e.dt_src = DT_HOST; e.check_finite = 0;
+  e.k_out = spp(nullptr); e.y_out = spp(nullptr); e.y0 = spp(nullptr); e.y1 = spp(nullptr);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) e.kprev[j] = spp(nullptr);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { e.beta[j] = 0.f; e.ebeta[j] = 0.f; }
+  e.ctrl = nullptr; e.dt_host = 0.f; e.rtol = 0.f; e.atol = 0.f; e.partials = nullptr;
+  e.n_peers = 0;
+#pragma unroll
+  for (int j = 0; j < kMaxPeers; ++j) e.peer_delta[j] = 0;
+  e.feat = nullptr; e.feat_mode = FEAT_OFF; e.feat_rank = 0; e.feat_row0 = 0; e.feat_hc_log2 = 0; e.feat_h_log2 = 0;
+  e.e_out = nullptr; e.err_prefix = 0;
+}
+
+// the zero-coefficient streams of a stage are not read (see drop_zero_terms in ndcn_api.cu: same rule, same bits)
+__device__ __forceinline__ void small_drop_zero_terms(EpiArgs& e) {
+  if (e.mode != EPI_LINCOMB && e.mode != EPI_ERR && e.mode != EPI_LINCOMB_E) return;
+  if (e.n_prev < 2 || e.err_prefix) return;
+  const bool two = e.mode == EPI_LINCOMB_E;
+  int w = 0;
+  for (int j = 0; j < e.n_prev; ++j) {
+    const bool zero = e.beta[j] == 0.0f && (!two || e.ebeta[j] == 0.0f);
+    if (zero && !(w == 0 && j == e.n_prev - 1)) continue;
+    e.kprev[w] = e.kprev[j];
+    e.beta[w] = e.beta[j];
+    e.ebeta[w] = e.ebeta[j];
+    ++w;
+  }
+  if (w == e.n_prev) return;
+  e.beta[w] = e.beta[e.n_prev];
+  e.ebeta[w] = e.ebeta[e.n_prev];
+  for (int j = w + 1; j < 8; ++j) e.beta[j] = e.ebeta[j] = 0.0f;
+  e.n_prev = w;
+}
+
+// relu((Phi x) W^T + b) for one row at H <= 32: one column per lane.  The loads of a row's neighbours are all in
+// flight together (the row's (col, val) pairs sit in the lanes and are broadcast by shuffle), the stage-algebra
+// streams are requested BEFORE the gather so that their latency overlaps it, and W^T comes from shared memory.
+// Same accumulation order as ndcn_any_row (CSR order; k = 0..H-1): bit-identical results.
+__device__ __forceinline__ void ndcn_row_narrow(const NdcnArgs& a, int H, const float* __restrict__ wt_s /* [H][33] */,
+                                                const float* __restrict__ x, float* zr, int64_t row, int lane,
+                                                const EpiCtx& c, double& err_acc) {
+  const bool act = lane < H;
+  EpiIn<1> in;
+  if (act) epi_load<1>(c, row * H + lane, in);
+  float s = 0.f;
+  if (a.flags & NDCN_F_NO_GRAPH) {
+    if (act) s = x[row * H + lane];
+  } else {
+    const int start = a.g.rowptr[row], end = a.g.rowptr[row + 1];
+    for (int base = start; base < end; base += 32) {
+      int my_c = 0;
+      float my_v = 0.f;
+      if (base + lane < end) {
+        my_c = __ldg(a.g.col + base + lane);
+        my_v = __ldg(a.g.val + base + lane);
+      }
+      const int cnt = min(32, end - base);
+      for (int j0 = 0; j0 < cnt; j0 += 8) {
+        float xv[8], vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cj = __shfl_sync(0xffffffffu, my_c, (j0 + u) & 31);
+          vv[u] = __shfl_sync(0xffffffffu, my_v, (j0 + u) & 31);
+          xv[u] = (act && j0 + u < cnt) ? x[(int64_t)cj * H + lane] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u < cnt) s = fmaf(vv[u], xv[u], s);
+      }
+    }
+  }
+  float kv[1] = {s};
+  if (!(a.flags & NDCN_F_NO_CONTROL)) {
+    if (act) zr[lane] = s;
+    __syncwarp();
+    float t = 0.f;
+    if (act) {
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) t = fmaf(zr[k], wt_s[k * 33 + lane], t);
+      kv[0] = t + __ldg(a.bias + lane);
+    }
+    __syncwarp();
+  }
+  if (!(a.flags & NDCN_F_NO_RELU)) kv[0] = fmaxf(kv[0], 0.f);
+  if (act) epi_math<1>(c, row * H + lane, kv, in, err_acc);
+}
+
+// one right-hand-side evaluation over all rows, fused with epilogue e (the launch-per-stage kernels' row code).
+//   VW > 0, CONTROL : relu((Phi x) W^T + b) at H = 32 VW NCH through k_stage_ndcn_gemm's 64-row tiles (gather -> SMEM
+//                     tile -> FP32-FMA GEMM with W^T streamed by cp.async.bulk -> bias/ReLU -> epilogue); `chunk_it` =
+//                     the CTA's running W^T chunk count (mbarrier phases)
+//   VW > 0, !CONTROL: no_control at the same widths: k_stage_ndcn_row's vectorised warp-per-row gather
+//   VW == 0         : one warp per row, any width, any right-hand side (H <= 32: ndcn_row_narrow)
+// `e` lives in shared memory (built by thread 0, published by a block barrier): no per-thread copies.
+template <int VW, int NCH, bool CONTROL>
+__device__ __noinline__ void small_stage(const SmallArgs& a, PtrPair src, const EpiArgs& e, float* zs,
+                                         const float* wt_s, uint32_t& chunk_it) {
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;  // finished solve: uniform over the grid
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  const float* __restrict__ x = sel(src, par);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double err_acc = 0.0;
+  const int64_t w0 = (int64_t)blockIdx.x * kWarpsPerCta + warp, wn = (int64_t)gridDim.x * kWarpsPerCta;
+  if (a.kind == NDCN_RHS_NDCN) {
+    NdcnArgs na;
+    na.g = a.g; na.x = src; na.Wt = a.Wt; na.bias = a.bias; na.flags = a.flags; na.long_rows = nullptr; na.n_long = 0;
+    if constexpr (VW > 0 && CONTROL) {
+      const int64_t n_tiles = ((int64_t)a.n_rows + kTileRows - 1) / kTileRows;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        ndcn_gemm_tile<VW, NCH>(na, c, x, tile * kTileRows, reinterpret_cast<unsigned char*>(zs), chunk_it, err_acc);
+    } else if constexpr (VW > 0) {
+      constexpr int H = 32 * VW * NCH;
+      const bool relu = !(a.flags & NDCN_F_NO_RELU);
+      for (int64_t row = w0; row < a.n_rows; row += wn) {
+        float acc[NCH][VW];
+        if (a.flags & NDCN_F_NO_GRAPH) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) ldv<VW>(x + row * H + ch * 32 * VW + lane * VW, acc[ch]);
+        } else {
+          gather_row<VW, NCH>(a.g, row, x, lane, acc);
+        }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < VW; ++i) acc[ch][i] = fmaxf(acc[ch][i], 0.f);
+          }
+          epi_apply<VW>(c, row * H + ch * 32 * VW + lane * VW, acc[ch], err_acc);
+        }
+      }
+    } else if (a.H <= 32) {
+      for (int64_t row = w0; row < a.n_rows; row += wn) ndcn_row_narrow(na, a.H, wt_s, x, zs + warp * 32, row, lane, c, err_acc);
+    } else {
+      for (int64_t row = w0; row < a.n_rows; row += wn) ndcn_any_row(na, a.H, a.W, x, zs + warp * a.H, row, lane, c, err_acc);
+    }
+  } else {
+    DynArgs da;
+    da.g = a.g; da.x = src; da.kind = a.kind; da.d = a.H;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) da.p[i] = a.p[i];
+    for (int64_t row = w0; row < a.n_rows; row += wn) {
+      if (a.H == 1) {
+        if (a.kind == NDCN_RHS_HEAT) dyn1_row_warp<NDCN_RHS_HEAT>(da, x, row, lane, c, err_acc);
+        else if (a.kind == NDCN_RHS_GENE) dyn1_row_warp<NDCN_RHS_GENE>(da, x, row, lane, c, err_acc);
+        else dyn1_row_warp<NDCN_RHS_MUTUAL>(da, x, row, lane, c, err_acc);
+      } else {
+        if (a.kind == NDCN_RHS_HEAT) dynv_row<NDCN_RHS_HEAT>(da, x, row, lane, c, err_acc);
+        else if (a.kind == NDCN_RHS_GENE) dynv_row<NDCN_RHS_GENE>(da, x, row, lane, c, err_acc);
+        else dynv_row<NDCN_RHS_MUTUAL>(da, x, row, lane, c, err_acc);
+      }
+    }
+  }
+  epi_finish_block(e, err_acc);
+}
+
+__device__ __noinline__ void small_epi_only(const SmallArgs& a, PtrPair k_in, const EpiArgs& e) {
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  double err_acc = 0.0;
+  const bool bad = epi_only_range(sel(k_in, par), a.numel, c, e.check_finite, a.vec,
+                                  (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, err_acc);
+  if (e.check_finite && bad && e.ctrl) atomicExch(&e.ctrl->status, NDCN_E_NONFINITE);
+}
+
+__device__ __forceinline__ void small_copy(const float* __restrict__ src, float* __restrict__ dst, int64_t numel) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+// out slice `slot` <- state y: a copy, or y W_d^T + b_d with the fused decoder
+__device__ __forceinline__ void small_put_state(const SmallArgs& a, int64_t slot, const float* y) {
+  if (a.dec_C > 0) {
+    decode_rows_range(y, a.n_rows, a.H, a.dec_W, a.dec_b, a.dec_C, a.out + slot * (int64_t)a.n_rows * a.dec_C,
+                      ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5,
+                      threadIdx.x & 31);
+  } else {
+    float* dst = a.out + slot * a.numel;
+    if (dst != y) small_copy(y, dst, a.numel);
+  }
+}
+
+// fixed-order sum of the per-CTA partials by block 0 (what k_controller / k_init_scalar do in their own launch)
+__device__ __forceinline__ double small_sum_partials(const double* partials, int n, int stride2, int q, double* s_tmp) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[stride2 * i + q];
+  s_tmp[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_tmp[threadIdx.x] += s_tmp[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = s_tmp[0];
+  __syncthreads();
+  return r;
+}
+
+// thread 0 edits the stage descriptor in shared memory; PUBLISH makes it visible to the CTA (the grid barrier
+// that follows every stage keeps the next edit from overtaking a reader)
+#define NDCN_T0 if (threadIdx.x == 0)
+#define NDCN_PUBLISH()                              \
+  do {                                              \
+    __syncthreads();                                \
+    NDCN_T0 {                                       \
+      s_run = s_e;                                  \
+      s_run.partials = a.partials;                  \
+      small_drop_zero_terms(s_run);                 \
+    }                                               \
+    __syncthreads();                                \
+  } while (0)
+
+template <int VW, int NCH, bool CONTROL>
+__global__ void __launch_bounds__(kStageThreads, (VW > 0 && CONTROL) ? 1 : 2)
+k_solve_small(const __grid_constant__ SmallArgs a) {
+  // VW == 0: [warps][max(H, 32)] scratch rows of the row-per-warp right-hand side; tiled GEMM: GemmSmem<VW, NCH>
+  extern __shared__ __align__(128) float zs[];
+  __shared__ double s_tmp[kStageThreads];
+  __shared__ float s_xs[kEmitMaxPerLaunch * 4];
+  __shared__ float s_wt[32 * 33];  // W^T of a narrow Linear (H <= 32), padded rows
+  __shared__ EpiArgs s_e, s_run;
+  cg::grid_group grid = cg::this_grid();
+  Ctrl* ctrl = a.ctrl;
+  uint32_t chunk_it = 0;
+  if constexpr (VW > 0 && CONTROL) ndcn_gemm_init_bars<VW, NCH>(reinterpret_cast<unsigned char*>(zs));
+  if (VW == 0 && a.kind == NDCN_RHS_NDCN && a.H <= 32 && !(a.flags & NDCN_F_NO_CONTROL)) {
+    for (int i = threadIdx.x; i < a.H * a.H; i += blockDim.x) {
+      const int n = i / a.H, k = i % a.H;
+      s_wt[k * 33 + n] = a.W[i];  // W[n][k] -> W^T[k][n]
+    }
+  }
+  __syncthreads();
+#define NDCN_STAGE(src) small_stage<VW, NCH, CONTROL>(a, src, s_run, zs, s_wt, chunk_it)
+
+  if (a.method != NDCN_DOPRI5) {
+    // ---------------- fixed grid: euler / midpoint / rk4 (3/8 rule), solvers.py:79-99 ----------------
+    float* cur = a.in_slab ? a.out : a.Y[0];
+    small_copy(a.y0, cur, a.numel);
+    if (!a.in_slab && !a.terminal) small_put_state(a, 0, a.y0);
+    grid.sync();
+    for (int i = 0; i + 1 < a.n_t; ++i) {
+      float* nxt = a.in_slab ? a.out + (int64_t)(i + 1) * a.numel : a.Y[(i + 1) & 1];
+      NDCN_T0 {
+        small_blank(s_e);
+        s_e.dt_src = DT_HOST;
+        s_e.dt_host = a.dts[i];
+        s_e.y0 = spp(cur);
+      }
+      if (a.method == NDCN_EULER) {  // fixed_grid.py:7-8
+        NDCN_T0 { s_e.mode = EPI_LINCOMB; s_e.beta[0] = 1.0f; s_e.y_out = spp(nxt); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(cur));
+        grid.sync();
+      } else if (a.method == NDCN_MIDPOINT) {  // fixed_grid.py:17-20
+        NDCN_T0 { s_e.mode = EPI_LINCOMB; s_e.beta[0] = 0.5f; s_e.y_out = spp(a.YS[0]); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(cur));
+        grid.sync();
+        NDCN_T0 { s_e.beta[0] = 1.0f; s_e.y_out = spp(nxt); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(a.YS[0]));
+        grid.sync();
+      } else {  // rk_common.py:72-78
+        NDCN_T0 { s_e.mode = EPI_RK4_1; s_e.k_out = spp(a.K[0]); s_e.y_out = spp(a.YS[0]); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(cur));
+        grid.sync();
+        NDCN_T0 { s_e.mode = EPI_RK4_2; s_e.k_out = spp(a.K[1]); s_e.kprev[0] = spp(a.K[0]); s_e.y_out = spp(a.YS[1]); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(a.YS[0]));
+        grid.sync();
+        NDCN_T0 { s_e.mode = EPI_RK4_3; s_e.k_out = spp(a.K[2]); s_e.kprev[1] = spp(a.K[1]); s_e.y_out = spp(a.YS[0]); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(a.YS[1]));
+        grid.sync();
+        NDCN_T0 { s_e.mode = EPI_RK4_4; s_e.k_out = spp(nullptr); s_e.kprev[2] = spp(a.K[2]); s_e.y_out = spp(nxt); }
+        NDCN_PUBLISH();
+        NDCN_STAGE(spp(a.YS[0]));
+        grid.sync();
+      }
+      // the new state goes to its output slot while the next step already reads it (nobody writes `nxt` again
+      // before the grid barrier that ends the next step)
+      if (!a.in_slab && !a.terminal) small_put_state(a, i + 1, nxt);
+      cur = nxt;
+    }
+    if (a.terminal) small_put_state(a, 0, cur);
+    return;
+  }
+
+  // ---------------- dopri5: solvers.py:25-33, dopri5.py:58-122 ----------------
+  const PtrPair Ycur = spp(a.Y[0], a.Y[1]), Yoth = spp(a.Y[1], a.Y[0]);
+  const PtrPair KFcur = spp(a.KF[0], a.KF[1]), KFoth = spp(a.KF[1], a.KF[0]);
+  small_copy(a.y0, a.Y[0], a.numel);
+  if (!a.terminal) small_put_state(a, 0, a.y0);
+  NDCN_T0 { small_blank(s_e); s_e.k_out = spp(a.KF[0]); }  // f0 = func(t0, y0)     dopri5.py:78
+  NDCN_PUBLISH();
+  grid.sync();
+  NDCN_STAGE(spp(a.Y[0]));
+  grid.sync();
+  if (!a.forced && !a.given_first) {
+    // _select_initial_step(order=4)     dopri5.py:80, misc.py:84-143
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    init_norms_block(a.Y[0], a.KF[0], nullptr, a.numel, a.rtol, a.atol, 0, a.partials, tid, stride);
+    grid.sync();
+    if (blockIdx.x == 0) {
+      const double s0 = small_sum_partials(a.partials, gridDim.x, 2, 0, s_tmp);
+      const double s1 = small_sum_partials(a.partials, gridDim.x, 2, 1, s_tmp);
+      if (threadIdx.x == 0) { init_scalar_decide(*ctrl, s0, s1, 0, a.t_first); __threadfence(); }
+    }
+    grid.sync();
+    NDCN_T0 {
+      small_blank(s_e);
+      s_e.ctrl = ctrl;
+      s_e.dt_src = DT_CTRL_H0;
+      s_e.mode = EPI_LINCOMB;
+      s_e.beta[0] = 1.0f;
+      s_e.y0 = spp(a.Y[0]);
+      s_e.y_out = spp(a.YS[0]);
+    }
+    NDCN_PUBLISH();
+    small_epi_only(a, spp(a.KF[0]), s_run);  // y0 + h0*f0
+    grid.sync();
+    NDCN_T0 { small_blank(s_e); s_e.k_out = spp(a.K[0]); }
+    NDCN_PUBLISH();
+    NDCN_STAGE(spp(a.YS[0]));
+    grid.sync();
+    init_norms_block(a.Y[0], a.KF[0], a.K[0], a.numel, a.rtol, a.atol, 1, a.partials, tid, stride);
+    grid.sync();
+    if (blockIdx.x == 0) {
+      const double s0 = small_sum_partials(a.partials, gridDim.x, 2, 0, s_tmp);
+      if (threadIdx.x == 0) { init_scalar_decide(*ctrl, s0, 0.0, 1, a.t_first); __threadfence(); }
+    }
+    grid.sync();
+  }
+
+  EmitArgs em;
+  em.ctrl = ctrl;
+  em.t_out = a.t_out;
+  em.y0 = Ycur;
+  em.y1 = Yoth;
+  em.k0 = KFcur;
+  em.k6 = KFoth;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) em.k[j] = a.K[j];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) em.c_mid[j] = a.c_mid[j];
+  em.out = a.out;
+  em.numel = a.numel;
+  em.dec_W = a.dec_C > 0 ? a.dec_W : nullptr;
+  em.dec_b = a.dec_C > 0 ? a.dec_b : nullptr;
+  em.dec_C = a.dec_C;
+  em.H = a.H;
+  em.n_rows = a.n_rows;
+
+  for (;;) {
+    if (((volatile Ctrl*)ctrl)->done) break;  // written before the last grid barrier: uniform
+    // stage input 1: y0 + (dt*b10) k0, k0 = FSAL derivative; also the finite-state guard (dopri5.py:101-102)
+    NDCN_T0 {
+      small_blank(s_e);
+      s_e.ctrl = ctrl;
+      s_e.dt_src = DT_CTRL;
+      s_e.y0 = Ycur;
+      s_e.mode = EPI_LINCOMB;
+      s_e.n_prev = 0;
+      s_e.beta[0] = a.beta32[0][0];
+      s_e.check_finite = 1;
+      s_e.y_out = spp(a.YS[0]);
+    }
+    NDCN_PUBLISH();
+    small_epi_only(a, KFcur, s_run);
+    grid.sync();
+    NDCN_T0 { s_e.check_finite = 0; s_e.kprev[0] = KFcur; }
+    for (int s = 1; s <= 5; ++s) {
+      NDCN_T0 {
+        s_e.n_prev = s;
+        for (int j = 0; j < 8; ++j) s_e.beta[j] = a.beta32[s][j];
+        s_e.k_out = spp(a.K[s - 1]);
+        if (s >= 2) s_e.kprev[s - 1] = spp(a.K[s - 2]);
+        s_e.y_out = (s < 5) ? spp(a.YS[s & 1]) : Yoth;  // stage 5 forms y1 (FSAL: c_sol == beta[-1])
+        if (s == 5 && a.err_prefix) {
+          s_e.mode = EPI_LINCOMB_E;
+          s_e.e_out = a.YS[1];
+          for (int j = 0; j < 8; ++j) s_e.ebeta[j] = j < 6 ? a.err32[j] : 0.0f;
+        }
+      }
+      NDCN_PUBLISH();
+      NDCN_STAGE(spp(a.YS[(s - 1) & 1]));
+      grid.sync();
+    }
+    // stage 6: k7 = f(y1) + error estimate
+    NDCN_T0 {
+      s_e.mode = EPI_ERR;
+      s_e.e_out = nullptr;
+      if (a.err_prefix) {
+        s_e.n_prev = 1;
+        s_e.err_prefix = 1;
+        for (int j = 0; j < 8; ++j) s_e.beta[j] = 0.0f;
+        s_e.beta[1] = a.err32[6];
+        s_e.kprev[0] = spp(a.YS[1]);
+      } else {
+        s_e.n_prev = 6;
+        for (int j = 0; j < 8; ++j) s_e.beta[j] = a.err32[j];
+        s_e.kprev[5] = spp(a.K[4]);
+      }
+      s_e.k_out = KFoth;
+      s_e.y_out = spp(nullptr);
+      s_e.y1 = Yoth;
+      s_e.rtol = a.rtol;
+      s_e.atol = a.atol;
+    }
+    NDCN_PUBLISH();
+    NDCN_STAGE(Yoth);
+    grid.sync();
+    // accept / reject + next step size: block 0 (k_controller's arithmetic)
+    if (blockIdx.x == 0) {
+      if (((volatile Ctrl*)ctrl)->status != 0) {  // non-finite state flagged by the pre-stage
+        if (threadIdx.x == 0) { ctrl->done = 1; ctrl->emit_lo = ctrl->emit_hi; }
+      } else {
+        const double sum = small_sum_partials(a.partials, gridDim.x, 1, 0, s_tmp);
+        if (threadIdx.x == 0) controller_decide(*ctrl, sum, a.t_out);
+      }
+      __threadfence();
+    }
+    grid.sync();
+    // dense output of the step just accepted, for the requested times inside it; reads y0/y1/k_j only, the next
+    // attempt's pre-stage writes YS[0] only: no barrier needed in between
+    if (a.dec_C > 0) emit_decode_range(em, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5);
+    else emit_range(em, a.vec, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, s_xs);
+  }
+#undef NDCN_STAGE
+}
+#undef NDCN_T0
+#undef NDCN_PUBLISH
+
+}  // namespace ndcn

@@ -162,28 +162,8 @@ __global__ void __launch_bounds__(kStageThreads) k_copy_slices(const float* __re
 //                 1 = only sum partials into xchg[0..1] (multi-GPU: the host hook all-reduces);
 //                 2 = decide from xchg[0] (after the all-reduce).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStageThreadsCtl) k_controller(Ctrl* ctrl, const double* partials, int n_partials,
-                                                                 const double* t_out, double* xchg, int reduce_stage) {
-  if (((volatile Ctrl*)ctrl)->done) {
-    // attempts enqueued past the end are no-ops: also retire the already-emitted outputs
-    if (threadIdx.x == 0) ctrl->emit_lo = ctrl->emit_hi;
-    return;
-  }
-  if (((volatile Ctrl*)ctrl)->status != 0) {  // e.g. non-finite state flagged by the pre-stage
-    if (threadIdx.x == 0) { ctrl->done = 1; ctrl->emit_lo = ctrl->emit_hi; }
-    return;
-  }
-  double sum = 0.0;
-  if (reduce_stage != 2) sum = block_sum_partials(partials, n_partials);
-  if (threadIdx.x != 0) return;
-  if (reduce_stage == 1) {
-    xchg[0] = sum;
-    xchg[1] = 0.0;
-    return;
-  }
-  if (reduce_stage == 2) sum = xchg[0];
-
-  Ctrl& c = *ctrl;
+// the float64 scalar work of one attempt (one thread), given the sum of squared error ratios
+__device__ __forceinline__ void controller_decide(Ctrl& c, double sum, const double* __restrict__ t_out) {
   c.sum_sq = sum;
   c.n_attempt += 1;
   // torch.mean of the squared ratios, an fp32 scalar   (misc.py:155-156)
@@ -243,6 +223,29 @@ __global__ void __launch_bounds__(kStageThreadsCtl) k_controller(Ctrl* ctrl, con
       c.done = 1;
     }
   }
+}
+
+__global__ void __launch_bounds__(kStageThreadsCtl) k_controller(Ctrl* ctrl, const double* partials, int n_partials,
+                                                                 const double* t_out, double* xchg, int reduce_stage) {
+  if (((volatile Ctrl*)ctrl)->done) {
+    // attempts enqueued past the end are no-ops: also retire the already-emitted outputs
+    if (threadIdx.x == 0) ctrl->emit_lo = ctrl->emit_hi;
+    return;
+  }
+  if (((volatile Ctrl*)ctrl)->status != 0) {  // e.g. non-finite state flagged by the pre-stage
+    if (threadIdx.x == 0) { ctrl->done = 1; ctrl->emit_lo = ctrl->emit_hi; }
+    return;
+  }
+  double sum = 0.0;
+  if (reduce_stage != 2) sum = block_sum_partials(partials, n_partials);
+  if (threadIdx.x != 0) return;
+  if (reduce_stage == 1) {
+    xchg[0] = sum;
+    xchg[1] = 0.0;
+    return;
+  }
+  if (reduce_stage == 2) sum = xchg[0];
+  controller_decide(*ctrl, sum, t_out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -311,7 +314,9 @@ __device__ __forceinline__ void emit_elem(const EmitArgs& a, const float* y0p, c
 
 constexpr int kEmitMaxPerLaunch = 32;
 
-__global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
+// dense output of the pending step for the elements [tid, numel) in steps of `stride` threads; every thread of the
+// CTA must call it (block barriers around the shared abscissa table `xs`, kEmitMaxPerLaunch * 4 floats)
+__device__ __forceinline__ void emit_range(const EmitArgs& a, int vec, int64_t tid, int64_t stride, float* xs) {
   const volatile Ctrl* ct = a.ctrl;
   const int lo0 = ct->emit_lo, hi0 = ct->emit_hi;
   if (lo0 >= hi0) return;
@@ -324,7 +329,6 @@ __global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
   const float* y1p = sel(a.y1, par);
   const float* k0p = sel(a.k0, par);
   const float* k6p = sel(a.k6, par);
-  __shared__ float xs[kEmitMaxPerLaunch * 4];
   for (int lo = lo0; lo < hi0; lo += kEmitMaxPerLaunch) {
     const int hi = min(hi0, lo + kEmitMaxPerLaunch);
     __syncthreads();
@@ -338,8 +342,6 @@ __global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
       p = fmul(p, x); xs[threadIdx.x * 4 + 3] = p;
     }
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
       const int64_t n4 = a.numel >> 2;
       for (int64_t i = tid; i < n4; i += stride)
@@ -351,6 +353,11 @@ __global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
         emit_elem<1>(a, y0p, y1p, k0p, k6p, i, dt, lo, hi, xs, terminal_only, n_out);
     }
   }
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_emit(EmitArgs a, int vec) {
+  __shared__ float xs[kEmitMaxPerLaunch * 4];
+  emit_range(a, vec, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, xs);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -371,14 +378,10 @@ __device__ __forceinline__ void decode_store(const float (&acc)[kDecMaxC], int C
   }
 }
 
-// out[r, :] = y[r, :] W_d^T + b_d    (slot 0 = y0, fixed-grid states, terminal states)
-__global__ void __launch_bounds__(kStageThreads) k_decode_rows(const float* __restrict__ y, int64_t n_rows, int H,
-                                                               const float* __restrict__ dec_W,
-                                                               const float* __restrict__ dec_b, int C,
-                                                               float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+// out[r, :] = y[r, :] W_d^T + b_d    (slot 0 = y0, fixed-grid states, terminal states); warps warp0, warp0 + n_warps, ...
+__device__ __forceinline__ void decode_rows_range(const float* __restrict__ y, int64_t n_rows, int H,
+                                                  const float* __restrict__ dec_W, const float* __restrict__ dec_b, int C,
+                                                  float* __restrict__ out, int64_t warp0, int64_t n_warps, int lane) {
   for (int64_t r = warp0; r < n_rows; r += n_warps) {
     float acc[kDecMaxC];
 #pragma unroll
@@ -393,8 +396,16 @@ __global__ void __launch_bounds__(kStageThreads) k_decode_rows(const float* __re
   }
 }
 
+__global__ void __launch_bounds__(kStageThreads) k_decode_rows(const float* __restrict__ y, int64_t n_rows, int H,
+                                                               const float* __restrict__ dec_W,
+                                                               const float* __restrict__ dec_b, int C,
+                                                               float* __restrict__ out) {
+  decode_rows_range(y, n_rows, H, dec_W, dec_b, C, out, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                    ((int64_t)gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
+}
+
 // dense output of the pending dopri5 step, decoded: same fit/evaluate arithmetic as emit_elem<1>
-__global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
+__device__ __forceinline__ void emit_decode_range(const EmitArgs& a, int64_t warp0, int64_t n_warps) {
   const volatile Ctrl* ct = a.ctrl;
   const int lo0 = ct->emit_lo, hi0 = ct->emit_hi;
   if (lo0 >= hi0) return;
@@ -408,8 +419,6 @@ __global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
   const float* k0p = sel(a.k0, par);
   const float* k6p = sel(a.k6, par);
   const int lane = threadIdx.x & 31, H = a.H, C = a.dec_C;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float m2dt = fmul(-2.f, dt), p2dt = fmul(2.f, dt), p5dt = fmul(5.f, dt), m3dt = fmul(-3.f, dt),
               m4dt = fmul(-4.f, dt);
   // outputs in groups of kJB: the nine streams of the step are read once per group, not once per output
@@ -474,18 +483,22 @@ __global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(kStageThreads) k_emit_decode(EmitArgs a) {
+  emit_decode_range(a, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5);
+}
+
 // ---------------------------------------------------------------------------------------
 // _select_initial_step (misc.py:84-143), fp32, RMS norms, order = 4 for dopri5.
 // ---------------------------------------------------------------------------------------
 // partials[2*b+0] += sum (u/scale)^2, partials[2*b+1] += sum (v/scale)^2, scale = atol+|y0|*rtol
 // mode 0: u = y0, v = f0          (d0, d1)
 // mode 1: u = f1 - f0, v unused   (d2)
-__global__ void __launch_bounds__(kStageThreads) k_init_norms(const float* y0, const float* f0, const float* f1,
-                                                              int64_t numel, float rtol, float atol, int mode,
-                                                              double* partials) {
+// every thread of the CTA must call it (block reduction); writes partials[2 * blockIdx.x + {0,1}]
+__device__ __forceinline__ void init_norms_block(const float* y0, const float* f0, const float* f1, int64_t numel,
+                                                 float rtol, float atol, int mode, double* partials, int64_t tid,
+                                                 int64_t stride) {
   double s0 = 0.0, s1 = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+  for (int64_t i = tid; i < numel; i += stride) {
     const float y = y0[i];
     const float scale = fadd(atol, fmul(fabsf(y), rtol));
     if (mode == 0) {
@@ -504,6 +517,7 @@ __global__ void __launch_bounds__(kStageThreads) k_init_norms(const float* y0, c
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // r0/r1 may still be read from an earlier call
   if (lane == 0) { r0[warp] = s0; r1[warp] = s1; }
   __syncthreads();
   if (warp == 0) {
@@ -515,6 +529,36 @@ __global__ void __launch_bounds__(kStageThreads) k_init_norms(const float* y0, c
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
     if (lane == 0) { partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b; }
+  }
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_init_norms(const float* y0, const float* f0, const float* f1,
+                                                              int64_t numel, float rtol, float atol, int mode,
+                                                              double* partials) {
+  init_norms_block(y0, f0, f1, numel, rtol, atol, mode, partials, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                   (int64_t)gridDim.x * blockDim.x);
+}
+
+// one thread: h0 from the norms d0, d1 (phase 0); dt from d1, d2 and the controller's start time (phase 1)
+__device__ __forceinline__ void init_scalar_decide(Ctrl& c, double sum0, double sum1, int phase, double t_first) {
+  const float rootn = (float)sqrt(c.numel_global);  // numel ** 0.5, a Python float -> fp32 divisor
+  if (phase == 0) {
+    const float d0 = fdiv((float)sqrt(sum0), rootn);
+    const float d1 = fdiv((float)sqrt(sum1), rootn);
+    c.d0 = d0;
+    c.d1 = d1;
+    c.h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : fmul(0.01f, fdiv(d0, d1));
+  } else {
+    const float h0 = c.h0, d1 = c.d1;
+    const float d2 = fdiv(fdiv((float)sqrt(sum0), rootn), h0);
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, fmul(h0, 1e-3f));
+    else h1 = powf(fdiv(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
+    const float h = fminf(fmul(100.f, h0), h1);
+    c.dt = (double)h;
+    c.first_step = (double)h;
+    c.t0 = c.t1 = t_first;
+    if (!(c.t1 + c.dt > c.t1)) { c.status = NDCN_E_DT_UNDERFLOW; c.done = 1; }
   }
 }
 
@@ -543,26 +587,7 @@ __global__ void __launch_bounds__(kStageThreadsCtl) k_init_scalar(Ctrl* ctrl, co
   if (threadIdx.x != 0) return;
   if (xchg_stage == 1) { xchg[0] = sums[0]; xchg[1] = sums[1]; return; }
   if (xchg_stage == 2) { sums[0] = xchg[0]; sums[1] = xchg[1]; }
-  Ctrl& c = *ctrl;
-  const float rootn = (float)sqrt(c.numel_global);  // numel ** 0.5, a Python float -> fp32 divisor
-  if (phase == 0) {
-    const float d0 = fdiv((float)sqrt(sums[0]), rootn);
-    const float d1 = fdiv((float)sqrt(sums[1]), rootn);
-    c.d0 = d0;
-    c.d1 = d1;
-    c.h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : fmul(0.01f, fdiv(d0, d1));
-  } else {
-    const float h0 = c.h0, d1 = c.d1;
-    const float d2 = fdiv(fdiv((float)sqrt(sums[0]), rootn), h0);
-    float h1;
-    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, fmul(h0, 1e-3f));
-    else h1 = powf(fdiv(0.01f, fmaxf(d1, d2)), 1.0f / 5.0f);
-    const float h = fminf(fmul(100.f, h0), h1);
-    c.dt = (double)h;
-    c.first_step = (double)h;
-    c.t0 = c.t1 = t_first;
-    if (!(c.t1 + c.dt > c.t1)) { c.status = NDCN_E_DT_UNDERFLOW; c.done = 1; }
-  }
+  init_scalar_decide(*ctrl, sums[0], sums[1], phase, t_first);
 }
 
 // error-ratio sum as a stand-alone op (C ABI ndcn_error_ratio_f32)
@@ -623,6 +648,88 @@ __global__ void k_transpose(const float* __restrict__ W, float* __restrict__ Wt,
     const int n = i / H, k = i % H;
     Wt[(size_t)k * H + n] = W[i];
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Parameter gradients of the Linear: dW[o][i] = sum_r gp[r][o] z[r][i], db[o] = sum_r gp[r][o]
+// (what autograd computes through nn.Linear, neural_dynamics.py:33).  Split over row chunks (blockIdx.z): every CTA
+// forms a 64x64 tile of the partial product of its chunk on FP32 FMA pipes (both operands are read as [rows, 64]
+// tiles, i.e. coalesced along H); k_weight_grads_reduce then adds the chunks in chunk order -> reproducible.
+// ---------------------------------------------------------------------------------------
+constexpr int kWgTile = 64;
+constexpr int kWgK = 16;
+
+__global__ void __launch_bounds__(256) k_weight_grads_partial(const float* __restrict__ gp, const float* __restrict__ z,
+                                                              int64_t n, int H, int64_t rows_per_chunk,
+                                                              float* __restrict__ part /* [nz][H][H] */,
+                                                              float* __restrict__ part_b /* [nz][H] or null */) {
+  __shared__ float As[kWgK][kWgTile + 4];
+  __shared__ float Bs[kWgK][kWgTile + 4];
+  const int o0 = blockIdx.y * kWgTile, i0 = blockIdx.x * kWgTile;
+  const int64_t r0 = (int64_t)blockIdx.z * rows_per_chunk;
+  const int64_t r1 = min(n, r0 + rows_per_chunk);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float bsum = 0.f;  // column sum of gp for db: threads ty == 0 .. of the i-tile 0 CTAs
+  const int lr = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;  // loader: 16 rows x 64 columns, 4 floats per thread
+  for (int64_t r = r0; r < r1; r += kWgK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t rr = r + lr;
+      float va = 0.f, vb = 0.f;
+      if (rr < r1) {
+        if (o0 + lc + q < H) va = gp[rr * H + o0 + lc + q];
+        if (i0 + lc + q < H) vb = z[rr * H + i0 + lc + q];
+      }
+      As[lr][lc + q] = va;
+      Bs[lr][lc + q] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kWgK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    if (part_b != nullptr && blockIdx.x == 0 && threadIdx.x < kWgTile) {
+#pragma unroll
+      for (int k = 0; k < kWgK; ++k) bsum += As[k][threadIdx.x];
+    }
+    __syncthreads();
+  }
+  float* dst = part + (size_t)blockIdx.z * H * H;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int o = o0 + ty * 4 + a;
+    if (o >= H) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + tx * 4 + b;
+      if (i < H) dst[(size_t)o * H + i] = acc[a][b];
+    }
+  }
+  if (part_b != nullptr && blockIdx.x == 0 && threadIdx.x < kWgTile && o0 + (int)threadIdx.x < H)
+    part_b[(size_t)blockIdx.z * H + o0 + threadIdx.x] = bsum;
+}
+
+// out[j] (+)= sum_c part[c][j], chunks added in order
+__global__ void __launch_bounds__(256) k_weight_grads_reduce(const float* __restrict__ part, int nz, int64_t count,
+                                                             float* __restrict__ out, int accumulate) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  float s = accumulate ? out[j] : 0.f;
+  for (int c = 0; c < nz; ++c) s += part[(size_t)c * count + j];
+  out[j] = s;
 }
 
 // out[q][r][c] = x[r][q * bc + c]: the row-sharded state as H / bc column blocks, block q being what

@@ -203,8 +203,13 @@ struct GemmSmem {
   static constexpr size_t total = z_bytes + w_bytes + 64;
 };
 
+// One tile of 64 rows starting at row0, by the whole CTA.  `chunk_it` counts the W^T chunks this CTA has consumed
+// so far (buffer = it & 1, mbarrier parity = (it >> 1) & 1): a persistent CTA may call this for tile after tile.
+// The caller has initialised bars[0..1] (count 1) and made the initialisation visible (mbar_fence_init + barrier).
 template <int VW, int NCH>
-__global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a, EpiArgs e) {
+__device__ __forceinline__ void ndcn_gemm_tile(const NdcnArgs& a, const EpiCtx& c, const float* __restrict__ x,
+                                               int64_t row0, unsigned char* smem_raw, uint32_t& chunk_it,
+                                               double& err_acc) {
   constexpr int H = 32 * VW * NCH;
   using S = GemmSmem<VW, NCH>;
   constexpr int ZLD = S::ZLD;
@@ -212,28 +217,20 @@ __global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a
   constexpr uint32_t kChunkBytes = kKChunk * H * sizeof(float);
   constexpr int RPW = kTileRows / kWarpsPerCta;  // rows per warp in the GEMM phase (8)
 
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* z = reinterpret_cast<float*>(smem_raw);
   float* wbuf = reinterpret_cast<float*>(smem_raw + S::z_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::z_bytes + S::w_bytes);
   int* row_counter = reinterpret_cast<int*>(bars + 2);
 
-  EpiCtx c;
-  if (!epi_resolve(e, c)) return;
-  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
-  const float* __restrict__ x = sel(a.x, par);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * kTileRows;
   const int rows_here = (int)min((int64_t)kTileRows, a.g.n_rows - row0);
+  const uint32_t it0 = chunk_it;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
     *row_counter = 0;
     // W^T chunk 0 lands while the tile is being gathered
-    mbar_arrive_expect_tx(&bars[0], kChunkBytes);
-    bulk_g2s(wbuf, a.Wt, kChunkBytes, &bars[0]);
+    mbar_arrive_expect_tx(&bars[it0 & 1], kChunkBytes);
+    bulk_g2s(wbuf + (it0 & 1) * kKChunk * H, a.Wt, kChunkBytes, &bars[it0 & 1]);
   }
   __syncthreads();
 
@@ -282,13 +279,14 @@ __global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a
 
   const float* zw = z + (warp * RPW) * ZLD;
   for (int kc = 0; kc < NCHUNKS; ++kc) {
+    const uint32_t it = it0 + (uint32_t)kc;
     if (threadIdx.x == 0 && kc + 1 < NCHUNKS) {
-      const int nb = (kc + 1) & 1;
+      const uint32_t nb = (it + 1) & 1;
       mbar_arrive_expect_tx(&bars[nb], kChunkBytes);
       bulk_g2s(wbuf + nb * kKChunk * H, a.Wt + (size_t)(kc + 1) * kKChunk * H, kChunkBytes, &bars[nb]);
     }
-    mbar_wait(&bars[kc & 1], (kc >> 1) & 1);
-    const float* wb = wbuf + (kc & 1) * kKChunk * H + lane * VW;
+    mbar_wait(&bars[it & 1], (it >> 1) & 1);
+    const float* wb = wbuf + (it & 1) * kKChunk * H + lane * VW;
 #pragma unroll
     for (int kk = 0; kk < kKChunk; kk += 4) {
       float4 av[RPW];
@@ -310,11 +308,11 @@ __global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a
         }
       }
     }
-    __syncthreads();  // everyone is done with wbuf[kc&1] before it is refilled
+    __syncthreads();  // everyone is done with this W buffer before it is refilled
   }
+  chunk_it = it0 + NCHUNKS;
 
   // ---- phase 3: bias, ReLU, stage epilogue ----
-  double err_acc = 0.0;
   float bv[NCH][VW];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) ldv<VW>(a.bias + ch * 32 * VW + lane * VW, bv[ch]);
@@ -335,6 +333,31 @@ __global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a
       }
     }
   }
+}
+
+template <int VW, int NCH>
+__device__ __forceinline__ void ndcn_gemm_init_bars(unsigned char* smem_raw) {
+  using S = GemmSmem<VW, NCH>;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + S::z_bytes + S::w_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+template <int VW, int NCH>
+__global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a, EpiArgs e) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  const float* __restrict__ x = sel(a.x, par);
+  ndcn_gemm_init_bars<VW, NCH>(smem_raw);
+  uint32_t chunk_it = 0;
+  double err_acc = 0.0;
+  ndcn_gemm_tile<VW, NCH>(a, c, x, (int64_t)blockIdx.x * kTileRows, smem_raw, chunk_it, err_acc);
   epi_finish_block(e, err_acc);
 }
 
@@ -344,6 +367,39 @@ __global__ void __launch_bounds__(kStageThreads, 2) k_stage_ndcn_gemm(NdcnArgs a
 // H=1 with --baseline no_embed heat_dynamics.py:251-256); throughput is irrelevant there
 // (N is a few hundred to a few thousand), launch count is what matters.
 // ---------------------------------------------------------------------------------------
+// one row of relu((Phi x) W^T + b) for any width, by one warp; zr = the warp's [H] scratch row in shared memory
+__device__ __forceinline__ void ndcn_any_row(const NdcnArgs& a, int H, const float* __restrict__ W,
+                                             const float* __restrict__ x, float* zr, int64_t row, int lane,
+                                             const EpiCtx& c, double& err_acc) {
+  if (a.flags & NDCN_F_NO_GRAPH) {
+    for (int col = lane; col < H; col += 32) zr[col] = x[row * H + col];
+  } else {
+    const int start = a.g.rowptr[row], end = a.g.rowptr[row + 1];
+    for (int col = lane; col < H; col += 32) {
+      float s = 0.f;
+      for (int j = start; j < end; ++j)
+        s = fmaf(__ldg(a.g.val + j), x[(int64_t)__ldg(a.g.col + j) * H + col], s);
+      zr[col] = s;
+    }
+  }
+  __syncwarp();
+  const bool relu = !(a.flags & NDCN_F_NO_RELU);
+  for (int n = lane; n < H; n += 32) {
+    float kv[1];
+    if (a.flags & NDCN_F_NO_CONTROL) {
+      kv[0] = zr[n];
+    } else {
+      float s = 0.f;
+      const float* wr = W + (size_t)n * H;
+      for (int k = 0; k < H; ++k) s = fmaf(zr[k], __ldg(wr + k), s);
+      kv[0] = s + __ldg(a.bias + n);
+    }
+    if (relu) kv[0] = fmaxf(kv[0], 0.f);
+    epi_apply<1>(c, row * H + n, kv, err_acc);
+  }
+  __syncwarp();  // zr is rewritten by the warp's next row
+}
+
 __global__ void __launch_bounds__(kStageThreads) k_stage_ndcn_any(NdcnArgs a, int H, const float* W, EpiArgs e) {
   extern __shared__ float zs[];  // [warps][H]
   EpiCtx c;
@@ -353,35 +409,7 @@ __global__ void __launch_bounds__(kStageThreads) k_stage_ndcn_any(NdcnArgs a, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp;
   double err_acc = 0.0;
-  if (row < a.g.n_rows) {
-    float* zr = zs + warp * H;
-    if (a.flags & NDCN_F_NO_GRAPH) {
-      for (int col = lane; col < H; col += 32) zr[col] = x[row * H + col];
-    } else {
-      const int start = a.g.rowptr[row], end = a.g.rowptr[row + 1];
-      for (int col = lane; col < H; col += 32) {
-        float s = 0.f;
-        for (int j = start; j < end; ++j)
-          s = fmaf(__ldg(a.g.val + j), x[(int64_t)__ldg(a.g.col + j) * H + col], s);
-        zr[col] = s;
-      }
-    }
-    __syncwarp();
-    const bool relu = !(a.flags & NDCN_F_NO_RELU);
-    for (int n = lane; n < H; n += 32) {
-      float kv[1];
-      if (a.flags & NDCN_F_NO_CONTROL) {
-        kv[0] = zr[n];
-      } else {
-        float s = 0.f;
-        const float* wr = W + (size_t)n * H;
-        for (int k = 0; k < H; ++k) s = fmaf(zr[k], __ldg(wr + k), s);
-        kv[0] = s + __ldg(a.bias + n);
-      }
-      if (relu) kv[0] = fmaxf(kv[0], 0.f);
-      epi_apply<1>(c, row * H + n, kv, err_acc);
-    }
-  }
+  if (row < a.g.n_rows) ndcn_any_row(a, H, W, x, zs + warp * H, row, lane, c, err_acc);
   epi_finish_block(e, err_acc);
 }
 
@@ -473,6 +501,41 @@ __global__ void __launch_bounds__(kStageThreads) k_stage_dyn1(DynArgs a, EpiArgs
 
 // [N,d] state, d > 1: one warp per row, lanes over the d columns.
 template <int KIND>
+__device__ __forceinline__ void dynv_row(const DynArgs& a, const float* __restrict__ x, int64_t row, int lane,
+                                         const EpiCtx& c, double& err_acc) {
+  const int d = a.d;
+  const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
+  for (int col = lane; col < d; col += 32) {
+    const float xi = x[row * d + col];
+    float s = 0.f;
+    for (int j = start; j < end; ++j) {
+      const float xj = x[(int64_t)__ldg(a.g.col + j) * d + col];
+      s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, xj, false));
+    }
+    float kv[1] = {dyn_local<KIND>(a.p, xi, s)};
+    epi_apply<1>(c, row * d + col, kv, err_acc);
+  }
+}
+
+// [N,1] state, one warp per row: the lanes stride over the row's entries, shuffle-reduce, lane 0 finishes
+// (the persistent small-graph solver's flavour; k_stage_dyn1 packs several rows into a warp instead)
+template <int KIND>
+__device__ __forceinline__ void dyn1_row_warp(const DynArgs& a, const float* __restrict__ x, int64_t row, int lane,
+                                              const EpiCtx& c, double& err_acc) {
+  const float xi = x[row];
+  const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
+  float s = 0.f;
+  for (int j = start + lane; j < end; j += 32)
+    s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, x[__ldg(a.g.col + j)], true));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = fadd(s, __shfl_xor_sync(0xffffffffu, s, o));
+  if (lane == 0) {
+    float kv[1] = {dyn_local<KIND>(a.p, xi, s)};
+    epi_apply<1>(c, row, kv, err_acc);
+  }
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(kStageThreads) k_stage_dynv(DynArgs a, EpiArgs e) {
   EpiCtx c;
   if (!epi_resolve(e, c)) return;
@@ -480,21 +543,8 @@ __global__ void __launch_bounds__(kStageThreads) k_stage_dynv(DynArgs a, EpiArgs
   const float* __restrict__ x = sel(a.x, par);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-  const int d = a.d;
   double err_acc = 0.0;
-  if (row < a.g.n_rows) {
-    const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
-    for (int col = lane; col < d; col += 32) {
-      const float xi = x[row * d + col];
-      float s = 0.f;
-      for (int j = start; j < end; ++j) {
-        const float xj = x[(int64_t)__ldg(a.g.col + j) * d + col];
-        s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, xj, false));
-      }
-      float kv[1] = {dyn_local<KIND>(a.p, xi, s)};
-      epi_apply<1>(c, row * d + col, kv, err_acc);
-    }
-  }
+  if (row < a.g.n_rows) dynv_row<KIND>(a, x, row, lane, c, err_acc);
   epi_finish_block(e, err_acc);
 }
 
@@ -503,19 +553,15 @@ __global__ void __launch_bounds__(kStageThreads) k_stage_dynv(DynArgs a, EpiArgs
 // the FSAL derivative), the initial-step probe y0 + h0*f0 (misc.py:132), and every stage of
 // a callback RHS.  Pure streaming, 16-byte accesses.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kStageThreads) k_epi_only(PtrPair k_in, int64_t numel, EpiArgs e, int vec) {
-  EpiCtx c;
-  if (!epi_resolve(e, c)) return;
-  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
-  const float* __restrict__ kin = sel(k_in, par);
-  double err_acc = 0.0;
+// the elements [tid, numel) in steps of `stride` threads; returns whether a non-finite y0 was seen (check_finite)
+__device__ __forceinline__ bool epi_only_range(const float* __restrict__ kin, int64_t numel, const EpiCtx& c,
+                                               int check_finite, int vec, int64_t tid, int64_t stride, double& err_acc) {
   bool bad = false;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = vec ? (numel >> 2) : 0;  // vec: every buffer 16-byte aligned
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  for (int64_t i = tid; i < n4; i += stride) {
     float kv[4];
     ldv<4>(kin + i * 4, kv);
-    if (e.check_finite) {
+    if (check_finite) {
       float yv[4];
       ldv<4>(c.y0 + i * 4, yv);
 #pragma unroll
@@ -523,11 +569,22 @@ __global__ void __launch_bounds__(kStageThreads) k_epi_only(PtrPair k_in, int64_
     }
     epi_apply<4>(c, i * 4, kv, err_acc);
   }
-  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+  for (int64_t i = (n4 << 2) + tid; i < numel; i += stride) {
     float kv[1] = {kin[i]};
-    if (e.check_finite) bad |= !isfinite(c.y0[i]);
+    if (check_finite) bad |= !isfinite(c.y0[i]);
     epi_apply<1>(c, i, kv, err_acc);
   }
+  return bad;
+}
+
+__global__ void __launch_bounds__(kStageThreads) k_epi_only(PtrPair k_in, int64_t numel, EpiArgs e, int vec) {
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  const float* __restrict__ kin = sel(k_in, par);
+  double err_acc = 0.0;
+  const bool bad = epi_only_range(kin, numel, c, e.check_finite, vec, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                                  (int64_t)gridDim.x * blockDim.x, err_acc);
   if (e.check_finite && bad && e.ctrl) {
     atomicExch(&e.ctrl->status, NDCN_E_NONFINITE);
   }

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from .odeint import odeint as _odeint
 from . import solver as _solver
-from .autograd_solver import SpmmFn
+from .autograd_solver import RhsFn, SpmmFn
 from .graph import cached_graph, require_cuda
 from .solver import RhsSpec
 
@@ -44,8 +44,10 @@ class ODEFunc(nn.Module):
             raise RuntimeError("ndcn_b200.ODEFunc.forward needs a CUDA state (got %s); run with --gpu 0 or call "
                                "odeint(), which stages CPU inputs of gradient-free solves itself" % x.device)
         active_dropout = self.training and self.dropout > 0
-        needs_grad = torch.is_grad_enabled() and (x.requires_grad or self.wt.weight.requires_grad)
-        if x.dim() == 2 and x.dtype == torch.float32 and not needs_grad and not active_dropout:
+        params = [p for p in self.wt.parameters()] if not self.no_control else []
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        fusable = x.dim() == 2 and x.dtype == torch.float32 and not active_dropout
+        if fusable and not needs_grad:
             # one fused kernel: gather + W GEMM + bias + ReLU
             graph = None if self.no_graph else cached_graph(self, self.A, dev)
             if graph is None:
@@ -54,9 +56,24 @@ class ODEFunc(nn.Module):
                                 None if self.no_control else self.wt.bias,
                                 no_graph=self.no_graph, no_control=self.no_control)
             return _solver.rhs_eval(graph, spec, x)
-        # differentiable composition: our SpMM kernel (fwd Phi x, bwd Phi^T g) + autograd ops
+        if fusable and (self.no_control or self.wt.bias is not None):
+            # one autograd node: fused forward, fused vjp + own dW/db reduction in backward
+            from . import _ffi
+            graph = _identity_graph(x.shape[0], dev) if self.no_graph else cached_graph(self, self.A, dev)
+            graph_t = graph if self.no_graph else graph.transpose()
+            flags = (_ffi.F_NO_GRAPH if self.no_graph else 0) | (_ffi.F_NO_CONTROL if self.no_control else 0)
+            W = self.wt.weight if not self.no_control else x.new_zeros(())
+            b = self.wt.bias if not self.no_control else x.new_zeros(())
+            return RhsFn.apply(x, W, b, graph, graph_t, flags)
+        # everything else (active dropout: RNG-dependent; non-fp32 or non-2-D states, which the reference's
+        # dtype-agnostic ATen path accepts, neural_dynamics.py:27-36): differentiable composition of our SpMM kernel
+        # (fp32 2-D) or torch's own sparse/dense product with autograd ops
         if not self.no_graph:
-            x = SpmmFn.apply(x, cached_graph(self, self.A, dev))
+            if x.dim() == 2 and x.dtype == torch.float32:
+                x = SpmmFn.apply(x, cached_graph(self, self.A, dev))
+            else:
+                A = self.A.to(device=x.device, dtype=x.dtype)
+                x = torch.sparse.mm(A, x) if A.is_sparse else torch.matmul(A, x)
         if not self.no_control:
             x = self.wt(x)
         x = self.dropout_layer(x)

@@ -46,13 +46,19 @@ class RhsSpec:
     def mutual(dim: int, b=0.1, k=5.0, c=1.0, d=5.0, e=0.9, h=0.1) -> "RhsSpec":
         return RhsSpec(_ffi.RHS_MUTUAL, dim, p=(float(b), float(k), float(c), float(d), float(e), float(h), 0.0, 0.0))
 
-    def to_c(self, keep: list) -> _ffi.RhsDesc:
+    def to_c(self, keep: list, prepare: bool = False) -> _ffi.RhsDesc:
+        """``prepare``: also hand over the derived weight forms (W^T, tf32 images), cached per weight version --
+        for the per-evaluation entry points (``rhs_eval`` / vjp); the solver derives its own once per solve."""
         d = _ffi.RhsDesc()
         d.kind, d.flags, d.H = self.kind, self.flags, self.H
         if self.W is not None:
             W = self.W.detach().to(torch.float32).contiguous()
             keep.append(W)
             d.W = W.data_ptr()
+            if prepare and self.kind == _ffi.RHS_NDCN and W.is_cuda:
+                prep = prepared_weights(self.W, W)
+                keep.append(prep)
+                d.prepared = prep.data_ptr()
         if self.b is not None:
             b = self.b.detach().to(torch.float32).contiguous()
             keep.append(b)
@@ -83,6 +89,44 @@ class SolveInfo:
 
 
 last_solve_info: Optional[SolveInfo] = None
+
+_PREPARED: Dict[tuple, torch.Tensor] = {}
+
+
+def prepared_weights(W_param: torch.Tensor, W32: torch.Tensor) -> torch.Tensor:
+    """Device buffer with the derived forms of an ``nn.Linear`` weight the kernels consume (``ndcn_prepare_weights_f32``),
+    cached on (storage, in-place version): an optimiser step bumps the version, so a training iteration prepares
+    once and its dozens of RHS evaluations / vjps reuse the buffer."""
+    key = (W_param.data_ptr(), W_param._version, tuple(W_param.shape), str(W_param.device))
+    buf = _PREPARED.get(key)
+    if buf is None:
+        if len(_PREPARED) >= 8:
+            _PREPARED.pop(next(iter(_PREPARED)))
+        lib = _ffi.lib()
+        H = int(W32.shape[0])
+        nbytes = int(lib.ndcn_prepared_weights_bytes(H))
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=W32.device)
+        off = (-raw.data_ptr()) % 1024
+        buf = raw[off:off + nbytes]
+        with torch.cuda.device(W32.device):
+            _ffi.check(lib.ndcn_prepare_weights_f32(W32.data_ptr(), H, buf.data_ptr(), current_stream_ptr(W32.device)),
+                       "ndcn_prepare_weights_f32")
+        _PREPARED[key] = buf
+    return buf
+
+
+def weight_grads(gp: torch.Tensor, z: torch.Tensor, dW: torch.Tensor, db: Optional[torch.Tensor],
+                 accumulate: bool = True) -> None:
+    """dW (+)= gp^T z, db (+)= column sums of gp on the library's own reduction kernels (``ndcn_weight_grads_f32``):
+    the parameter gradients of ODEFunc's Linear (neural_dynamics.py:33) from what the RHS vjp leaves behind."""
+    assert gp.is_cuda and gp.dtype == torch.float32 and gp.is_contiguous() and z.is_contiguous() and gp.shape == z.shape
+    n, H = gp.shape
+    assert dW.shape == (H, H) and dW.is_contiguous() and dW.dtype == torch.float32
+    with torch.cuda.device(gp.device):
+        rc = _ffi.lib().ndcn_weight_grads_f32(gp.data_ptr(), z.data_ptr(), n, H, dW.data_ptr(),
+                                              db.data_ptr() if db is not None else None, 1 if accumulate else 0,
+                                              current_stream_ptr(gp.device))
+    _ffi.check(rc, "ndcn_weight_grads_f32")
 
 _WORKSPACES: Dict[Tuple[str, int], torch.Tensor] = {}
 
@@ -123,7 +167,7 @@ def rhs_eval(graph: CsrGraph, spec: RhsSpec, x: torch.Tensor) -> torch.Tensor:
                          (tuple(x.shape), graph.n_cols, spec.H))
     out = torch.empty((graph.n_rows, spec.H), dtype=torch.float32, device=x.device)
     keep: list = []
-    desc = spec.to_c(keep)
+    desc = spec.to_c(keep, prepare=True)
     with torch.cuda.device(x.device):
         rc = _ffi.lib().ndcn_rhs_eval_f32(graph.handle, C.byref(desc), x.data_ptr(), out.data_ptr(),
                                           current_stream_ptr(x.device))
@@ -143,7 +187,7 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
                  time_kernels: bool = False, first_step: Optional[float] = None, safety: float = 0.0,
                  ifactor: float = 0.0, dfactor: float = 0.0, z_block_cols: int = 0,
                  decoder: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None,
-                 peers=None) -> torch.Tensor:
+                 peers=None, small: Optional[bool] = None) -> torch.Tensor:
     """``torchdiffeq.odeint`` for a recognised RHS, entirely inside the CUDA library.
 
     y0: [n_rows, H] fp32 CUDA.  t: 1-D float tensor (any device); the values are used as
@@ -157,6 +201,9 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
     ``partition.FeaturePushPartition`` -- the peer-push schemes (no hook: the solve runs in the partition's IPC-shared workspace and the library's
     kernels store new gather-source rows straight into the other ranks' buffers); ``graph`` must be
     ``peers.graph`` and every rank must make the same calls in the same order.
+    ``small``: None = ``ndcn_odeint_f32`` (takes the persistent whole-solve kernel by itself when the problem is small
+    enough), True = require that kernel (``ndcn_odeint_small_f32``: ONE cooperative launch for the whole solve),
+    False = always one launch per stage (``ndcn_odeint_staged_f32``).
     """
     global last_solve_info
     if method not in _ffi.METHODS:
@@ -248,8 +295,10 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
             handle = entry[0]
         try:
             t_ptr = C.cast(t64.data_ptr(), _ffi.c_double_p)
-            rc = lib.ndcn_odeint_f32(handle, y0.data_ptr(), t_ptr, n_t, out.data_ptr(), C.byref(opts),
-                                     C.byref(stats), current_stream_ptr(dev))
+            entry = lib.ndcn_odeint_f32 if small is None else (lib.ndcn_odeint_small_f32 if small else
+                                                               lib.ndcn_odeint_staged_f32)
+            rc = entry(handle, y0.data_ptr(), t_ptr, n_t, out.data_ptr(), C.byref(opts), C.byref(stats),
+                       current_stream_ptr(dev))
         finally:
             if spec.callback is not None:
                 lib.ndcn_solver_destroy(handle)
