@@ -136,6 +136,20 @@ int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, const ndcn_
 int ndcn_weight_grads_f32(const float* gp, const float* z, int64_t n, int32_t H, float* dW, float* db,
                           int32_t accumulate, ndcn_stream_t s);
 
+/* Backward pass of a fixed-grid solve (euler | midpoint | rk4) for the narrow widths of the dynamics scripts (H <= 32,
+ * heat_dynamics.py:33) as ONE cooperative launch: what `loss.backward()` computes through odeint's step loop
+ * (solvers.py:79-99, rk_common.py:72-78; training loops heat_dynamics.py:317-334), i.e. the discrete adjoint of the scheme.
+ *   slab    [n_t, N, H]  the states the forward solve returned (out of ndcn_odeint_f32 on the same grid)
+ *   g_slab  [n_t, N, H]  cotangents of those outputs
+ *   lam     [N, H]       out: dL/dy0
+ *   dW [H,H], db [H]     out: parameter gradients of ODEFunc's Linear (ignored with NDCN_F_NO_CONTROL)
+ * Every stage of every step is recomputed from the slab; dW / db are accumulated in registers over all steps and
+ * reduced once in a fixed order.  NDCN right-hand sides, single-GPU graphs with at most 16384 rows; anything else
+ * returns NDCN_E_ARG (callers fall back to ndcn_rhs_vjp_f32 + ndcn_weight_grads_f32 step by step).            */
+int ndcn_fixed_grid_adjoint_small_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, const ndcn_rhs_desc_t* rhs,
+                                      int32_t method, const double* t_host, int32_t n_t, const float* slab,
+                                      const float* g_slab, float* lam, float* dW, float* db, ndcn_stream_t s);
+
 /* ---- solver -------------------------------------------------------------------------- */
 enum ndcn_method { NDCN_EULER = 0, NDCN_MIDPOINT = 1, NDCN_RK4 = 2, NDCN_DOPRI5 = 3 };
 

@@ -94,6 +94,9 @@ PROTOTYPES = {
     "ndcn_prepare_weights_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ndcn_weight_grads_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p]),
+    "ndcn_fixed_grid_adjoint_small_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RhsDesc), C.c_int32, c_double_p,
+                                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p]),
     "ndcn_solver_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "ndcn_solver_create": (C.c_int, [C.c_void_p, C.POINTER(RhsDesc), C.c_int32, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_void_p)]),

@@ -64,7 +64,7 @@ class RhsFn(torch.autograd.Function):
         spec = _solver.RhsSpec(_ffi.RHS_NDCN, int(x.shape[1]), flags, None if no_control else W, None if no_control else b)
         ctx.save_for_backward(x, W, b)
         ctx.graph, ctx.graph_t, ctx.flags = graph, graph_t, flags
-        return _solver.rhs_eval(graph, spec, x.contiguous())
+        return _solver.rhs_eval(graph, spec, x.contiguous(), cache_weights=True)
 
     @staticmethod
     def backward(ctx, gk):
@@ -241,7 +241,7 @@ def solve(func: Callable, y0: torch.Tensor, t: torch.Tensor, rtol: float, atol: 
 # GEMM / reduction calls.  dopri5 keeps the op-by-op autograd path above: its step-size controller is
 # part of the reference's autograd graph (misc.py:160-170), which a hand-written adjoint would drop.
 # ------------------------------------------------------------------------------------------------
-def _vjp(graph: CsrGraph, graph_t: CsrGraph, spec, x, gk, scale: float, gx, accumulate: bool):
+def _vjp(graph: CsrGraph, graph_t: CsrGraph, spec, x, gk, scale: float, gx, accumulate: bool, cache_weights: bool = True):
     """(gp, z): gx (+)= d<gk*scale, f(x)>/dx;  dW = gp^T z, db = gp.sum(0) are left to the caller."""
     import ctypes as C
 
@@ -250,7 +250,7 @@ def _vjp(graph: CsrGraph, graph_t: CsrGraph, spec, x, gk, scale: float, gx, accu
     gp = torch.empty_like(x)
     z = torch.empty_like(x) if not (spec.flags & _ffi.F_NO_GRAPH) else x
     keep: list = []
-    desc = spec.to_c(keep, prepare=True)
+    desc = spec.to_c(keep, prepare=cache_weights)
     with torch.cuda.device(x.device):
         rc = _ffi.lib().ndcn_rhs_vjp_f32(graph.handle, graph_t.handle, C.byref(desc), x.data_ptr(), gk.data_ptr(),
                                          float(scale), gx.data_ptr(), 1 if accumulate else 0, gp.data_ptr(),
@@ -262,6 +262,8 @@ def _vjp(graph: CsrGraph, graph_t: CsrGraph, spec, x, gk, scale: float, gx, accu
 
 class FusedFixedGridFn(torch.autograd.Function):
     """``odeint`` for euler | midpoint | rk4 on a recognised ODEFunc, differentiable in (y0, W, b)."""
+
+    persistent_backward = True  # H <= 32, small graphs: one cooperative launch for the whole backward pass
 
     @staticmethod
     def forward(ctx, y0, W, b, t32, graph, graph_t, flags, method):
@@ -289,6 +291,24 @@ class FusedFixedGridFn(torch.autograd.Function):
         dW = torch.zeros_like(W) if not no_control else None
         db = torch.zeros_like(b) if not no_control else None
         tt = t32.detach().to("cpu", torch.float32)
+        if H <= 32 and graph.n_rows <= 16384 and FusedFixedGridFn.persistent_backward:
+            # the whole backward pass as one cooperative launch (csrc/small_solver.cuh::k_adjoint_small)
+            import ctypes as C
+
+            lam = torch.empty_like(g_slab[0])
+            keep: list = []
+            desc = spec.to_c(keep)
+            t64 = tt.to(torch.float64).contiguous()
+            with torch.cuda.device(slab.device):
+                rc = _ffi.lib().ndcn_fixed_grid_adjoint_small_f32(
+                    graph.handle, graph_t.handle, C.byref(desc), _ffi.METHODS[method],
+                    C.cast(t64.data_ptr(), _ffi.c_double_p), int(t64.numel()), slab.data_ptr(), g_slab.data_ptr(),
+                    lam.data_ptr(), dW.data_ptr() if dW is not None else None, db.data_ptr() if db is not None else None,
+                    _solver.current_stream_ptr(slab.device))
+            if rc == 0:
+                return lam, dW, db, None, None, None, None, None
+            if rc != _ffi.E_ARG:
+                _ffi.check(rc, "ndcn_fixed_grid_adjoint_small_f32")
         lam = g_slab[-1].clone()
 
         def f(x):

@@ -223,6 +223,7 @@ struct ndcn_solver {
   float* Z_own = nullptr;              // workspace Z, restored when the scheme is switched off
   int feat_rank = 0, feat_world = 0, feat_hc = 0;
   int feat_bounds[9] = {};
+  bool feat_slab = true;               // slice buffers column-blocked [Hc/16][N][16] + k_gather_slab (NDCN_FEAT_SLAB=0: off)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -942,6 +943,96 @@ extern "C" int ndcn_rhs_vjp_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t, 
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------
+// discrete adjoint of a fixed-grid solve as ONE cooperative launch (narrow widths, small graphs)
+// ---------------------------------------------------------------------------------------
+extern "C" int ndcn_fixed_grid_adjoint_small_f32(const ndcn_graph_t* g, const ndcn_graph_t* g_t,
+                                                 const ndcn_rhs_desc_t* rhs, int32_t method, const double* t_host,
+                                                 int32_t n_t, const float* slab, const float* g_slab, float* lam,
+                                                 float* dW, float* db, ndcn_stream_t s) {
+  if (!g || !g_t || !rhs || !t_host || !slab || !g_slab || !lam || n_t < 2) return NDCN_E_ARG;
+  if (rhs->kind != NDCN_RHS_NDCN || rhs->H < 1 || rhs->H > 32) return NDCN_E_ARG;
+  if (method != NDCN_EULER && method != NDCN_MIDPOINT && method != NDCN_RK4) return NDCN_E_METHOD;
+  const bool no_control = (rhs->flags & NDCN_F_NO_CONTROL) != 0;
+  if (!no_control && (!rhs->W || !rhs->b || !dW || !db)) return NDCN_E_ARG;
+  const int64_t n = g->v.n_rows;
+  if (n < 1 || g->v.n_cols != n || g_t->v.n_rows != n || g_t->v.n_cols != n) return NDCN_E_ARG;
+  if (n > cfg().small_max_rows) return NDCN_E_ARG;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, current_device()) != cudaSuccess || !coop) return NDCN_E_ARG;
+  keep_scratch_pooled();
+  cudaStream_t st = (cudaStream_t)s;
+  const int H = rhs->H;
+  const int64_t numel = n * H;
+  const int sm_count = sm_count_now();
+
+  const size_t smem = sizeof(float) * kWarpsPerCta * 64;
+  int per_sm = 0;
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adjoint_small, kStageThreads, smem));
+  if (per_sm < 1) return NDCN_E_ARG;
+  const int by_rows = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta);
+  const int grid = std::max(1, std::min(by_rows, std::min(per_sm * sm_count, 2 * sm_count)));
+  const int64_t n_warps = (int64_t)grid * kWarpsPerCta;
+
+  // scratch: step sizes | U | up to 8 state-sized buffers | per-warp parameter-gradient partials
+  const size_t state_b = align_up(sizeof(float) * (size_t)numel, 256);
+  const int n_states = method == NDCN_RK4 ? 8 : (method == NDCN_MIDPOINT ? 2 : 0);
+  const size_t dts_b = align_up(sizeof(float) * (size_t)n_t, 256);
+  const size_t part_b = no_control ? 0 : align_up(sizeof(float) * (size_t)n_warps * (H * H + H), 256);
+  unsigned char* scratch = nullptr;
+  CU_TRY(cudaMallocAsync((void**)&scratch, dts_b + (1 + n_states) * state_b + part_b + 256, st));
+  unsigned char* p = (unsigned char*)align_up((size_t)scratch, 256);
+  float* dts_dev = (float*)p;
+  p += dts_b;
+  std::vector<float> dts((size_t)n_t - 1);
+  for (int i = 0; i + 1 < n_t; ++i) dts[i] = (float)t_host[i + 1] - (float)t_host[i];
+  cudaError_t ce = cudaMemcpyAsync(dts_dev, dts.data(), sizeof(float) * dts.size(), cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // `dts` is a host temporary
+  if (ce != cudaSuccess) {
+    cudaFreeAsync(scratch, st);
+    return (int)ce;
+  }
+  AdjArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.g = g->v;
+  a.gt = g_t->v;
+  a.H = H;
+  a.n_rows = (int)n;
+  a.n_t = n_t;
+  a.method = method;
+  a.flags = rhs->flags;
+  a.W = rhs->W;
+  a.bias = rhs->b;
+  a.dts = dts_dev;
+  a.slab = slab;
+  a.g_slab = g_slab;
+  a.lam = lam;
+  a.U = (float*)p;
+  p += state_b;
+  for (int i = 0; i < n_states; ++i) {
+    a.S[i] = (float*)p;
+    p += state_b;
+  }
+  a.part = no_control ? nullptr : (float*)p;
+  a.dW = dW;
+  a.db = db;
+  a.numel = numel;
+  SmallArgs fw;  // the forward right-hand side, for the stage recomputation
+  std::memset(&fw, 0, sizeof(fw));
+  fw.g = g->v;
+  fw.kind = NDCN_RHS_NDCN;
+  fw.H = H;
+  fw.flags = rhs->flags;
+  fw.W = rhs->W;
+  fw.bias = rhs->b;
+  fw.numel = numel;
+  fw.n_rows = (int)n;
+  void* params[] = {&a, &fw};
+  ce = cudaLaunchCooperativeKernel((void*)k_adjoint_small, dim3(grid), dim3(kStageThreads), params, smem, st);
+  cudaFreeAsync(scratch, st);
+  return (int)ce;
+}
+
 extern "C" int ndcn_spmm_f32(const ndcn_graph_t* g, const float* x, float* y, int32_t H, ndcn_stream_t s) {
   ndcn_rhs_desc_t r;
   std::memset(&r, 0, sizeof(r));
@@ -1188,7 +1279,17 @@ struct Driver : StageTimer {
       se.ctrl = e.ctrl;
       fill_feat(se, FEAT_Z_OWNERS);
       t_begin(NDCN_K_GATHER);
-      const int rcg = launch_stage(bg, pp(sv->xcs_self), se, nullptr, st);
+      int rcg = 0;
+      if (sv->feat_slab) {
+        const ndcn_graph* fg = sv->full_graph;
+        const int n_rb = (int)((fg->v.n_rows + kSlabRows - 1) / kSlabRows);
+        const int64_t grid = (int64_t)(sv->feat_hc / 16) * (n_rb + fg->n_long);
+        sv->launches += 1;
+        k_gather_slab<<<(unsigned)grid, kStageThreads, 0, st>>>(fg->v, sv->xcs_self, fg->v.n_cols, n_rb, fg->n_long, fg->long_rows, se);
+        rcg = (int)cudaGetLastError();
+      } else {
+        rcg = launch_stage(bg, pp(sv->xcs_self), se, nullptr, st);
+      }
       t_end();
       if (rcg != 0) return rcg;
       RC_TRY(peer_barrier(nullptr));  // every block of Z has arrived
@@ -1673,7 +1774,8 @@ static int run_small(Driver& d, const float* y0, const double* t, int n_t, float
   const bool wide = sv->rhs.kind == NDCN_RHS_NDCN && fast_width(sv->H) && sv->H > 32 && aligned16(y0) && aligned16(out);
   const bool tiled = wide && !(sv->rhs.flags & NDCN_F_NO_CONTROL);
   const bool rowvec = wide && (sv->rhs.flags & NDCN_F_NO_CONTROL);
-  const int by_rows = (int)((sv->n_rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  const bool dyn1 = sv->rhs.kind != NDCN_RHS_NDCN && sv->H == 1;  // 8 rows per warp
+  const int by_rows = (int)((sv->n_rows + (dyn1 ? 64 : kWarpsPerCta) - 1) / (dyn1 ? 64 : kWarpsPerCta));
   const int by_tiles = (int)((sv->n_rows + kTileRows - 1) / kTileRows);
   const int by_elems = (int)((sv->numel + kStageThreads * 4 - 1) / (kStageThreads * 4));
   const int want = std::max(tiled ? by_tiles : std::min(by_rows, 4 * sv->sm_count), std::min(by_elems, sv->sm_count));
@@ -1731,9 +1833,12 @@ static int odeint_impl(ndcn_solver_t* sv, const float* y0, const double* t_host,
 
   const bool small_ok = small_eligible(sv, opts);
   if (small_mode == 1 && !small_ok) return NDCN_E_ARG;
-  // auto: only where the launch-per-stage path would not run its tcgen05 kernels anyway
+  // auto: where the persistent kernel measured faster than a launch per stage on B200 (profiles/README.md): the
+  // narrow NDCN widths of the dynamics scripts (H <= 32) and the [N,1] ground-truth dynamics; the wide Cora block
+  // (H = 256) runs as fast launch by launch (its phases are long enough to hide the launch latency)
+  const bool small_pays = (sv->rhs.kind == NDCN_RHS_NDCN && sv->H <= 32) || (sv->rhs.kind != NDCN_RHS_NDCN && sv->H == 1);
   const bool use_small = n_t > 1 && small_ok &&
-                         (small_mode == 1 || (small_mode == 0 && cfg().small_solver && !umma_eligible(sv->rhs, sv->n_rows)));
+                         (small_mode == 1 || (small_mode == 0 && cfg().small_solver && small_pays));
   const bool fast_h = sv->H == 256 || sv->H == 128 || sv->H == 64 || sv->H == 32;
   if (sv->rhs.kind == NDCN_RHS_NDCN && !(sv->rhs.flags & NDCN_F_NO_CONTROL) && fast_h) {
     const int n = sv->H * sv->H;
@@ -1872,6 +1977,9 @@ extern "C" int ndcn_solver_set_feature_peers(ndcn_solver_t* sv, const ndcn_graph
   for (int r = 0; r <= 8; ++r) t.bounds[r] = (int)cfg->row_bounds[r <= P ? r : P];
   t.world = P;
   t.n_total = (int)cfg->row_bounds[P];
+  sv->feat_slab = true;
+  if (const char* v = std::getenv("NDCN_FEAT_SLAB")) sv->feat_slab = std::atoi(v) != 0;
+  t.slab = sv->feat_slab ? 1 : 0;
   t.nl_uniform = (int)(cfg->row_bounds[1] - cfg->row_bounds[0]);
   for (int r = 0; r < P; ++r) {
     const int64_t want = std::min<int64_t>((int64_t)r * t.nl_uniform, t.n_total);

@@ -72,6 +72,8 @@ struct FeatTable {
   int world;
   int nl_uniform; // > 0: every block but the last has exactly this many rows (owner = row / nl_uniform)
   int n_total;    // all rows
+  int slab;       // 1: slice buffers are column-blocked [Hc/16][N][16] (one 16-column slab = N*64 B contiguous, L2-sized
+                  //    at N = 1M: k_gather_slab walks it slab by slab); 0: row-major [N][Hc]
 };
 enum FeatMode : int { FEAT_OFF = 0, FEAT_Y_SLICES = 1, FEAT_Z_OWNERS = 2 };
 
@@ -238,7 +240,10 @@ __device__ __noinline__ void store_y_slices(const FeatTable* __restrict__ f, int
                                             int64_t off, float v0, float v1, float v2, float v3) {
   const int64_t row = off >> h_log2;
   const int col = (int)(off & (((int64_t)1 << h_log2) - 1));
-  float* dst = f->xcs[col >> hc_log2] + (((int64_t)row0 + row) << hc_log2) + (col & ((1 << hc_log2) - 1));
+  const int cs = col & ((1 << hc_log2) - 1);  // column inside the owner's slice
+  float* dst = f->xcs[col >> hc_log2];
+  if (f->slab) dst += (((int64_t)(cs >> 4) * f->n_total + row0 + row) << 4) + (cs & 15);
+  else dst += (((int64_t)row0 + row) << hc_log2) + cs;
   if constexpr (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
   else if constexpr (VW == 2) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
   else *dst = v0;

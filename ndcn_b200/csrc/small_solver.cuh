@@ -209,12 +209,16 @@ __device__ __noinline__ void small_stage(const SmallArgs& a, PtrPair src, const 
     da.g = a.g; da.x = src; da.kind = a.kind; da.d = a.H;
 #pragma unroll
     for (int i = 0; i < 8; ++i) da.p[i] = a.p[i];
-    for (int64_t row = w0; row < a.n_rows; row += wn) {
-      if (a.H == 1) {
-        if (a.kind == NDCN_RHS_HEAT) dyn1_row_warp<NDCN_RHS_HEAT>(da, x, row, lane, c, err_acc);
-        else if (a.kind == NDCN_RHS_GENE) dyn1_row_warp<NDCN_RHS_GENE>(da, x, row, lane, c, err_acc);
-        else dyn1_row_warp<NDCN_RHS_MUTUAL>(da, x, row, lane, c, err_acc);
-      } else {
+    if (a.H == 1) {
+      // k_stage_dyn1's row code: 4 lanes per row, 8 rows per warp
+      const int64_t n_w = ((int64_t)a.n_rows + 7) / 8;
+      for (int64_t w = w0; w < n_w; w += wn) {
+        if (a.kind == NDCN_RHS_HEAT) dyn1_warp_rows<NDCN_RHS_HEAT, 4>(da, x, w, lane, c, err_acc);
+        else if (a.kind == NDCN_RHS_GENE) dyn1_warp_rows<NDCN_RHS_GENE, 4>(da, x, w, lane, c, err_acc);
+        else dyn1_warp_rows<NDCN_RHS_MUTUAL, 4>(da, x, w, lane, c, err_acc);
+      }
+    } else {
+      for (int64_t row = w0; row < a.n_rows; row += wn) {
         if (a.kind == NDCN_RHS_HEAT) dynv_row<NDCN_RHS_HEAT>(da, x, row, lane, c, err_acc);
         else if (a.kind == NDCN_RHS_GENE) dynv_row<NDCN_RHS_GENE>(da, x, row, lane, c, err_acc);
         else dynv_row<NDCN_RHS_MUTUAL>(da, x, row, lane, c, err_acc);
@@ -501,5 +505,263 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
 }
 #undef NDCN_T0
 #undef NDCN_PUBLISH
+
+// =========================================================================================================
+// Persistent discrete adjoint of the fixed-grid solvers for the narrow widths of the dynamics scripts (H <= 32):
+// the backward pass of `loss.backward()` through odeint (heat_dynamics.py:317-334, `--method euler` default) as ONE
+// cooperative launch.  For every grid step, last to first, the step's stages are recomputed from the saved state
+// slab and each RHS evaluation k = relu((Phi x) W^T + b) is differentiated in two row-local phases
+//   P1  z = Phi x, mask = (pre-activation > 0), gp = scale * gk (.) mask, u = gp W, dW += gp^T z, db += sum gp
+//   P2  out = sum of the given addends + Phi^T u
+// (what autograd records through solvers.py:79-99 / rk_common.py:72-78, up to fp32 summation order).  The dW / db
+// contributions stay in the warps' registers over ALL steps and are reduced once, in warp order, at the end.
+// =========================================================================================================
+struct AdjArgs {
+  GraphView g, gt;        // Phi and Phi^T (pass g twice for a symmetric operator)
+  int H, n_rows, n_t, method;
+  uint32_t flags;
+  const float* W;         // [H,H]
+  const float* bias;      // [H]
+  const float* dts;       // [n_t - 1]
+  const float* slab;      // [n_t, N, H] forward states
+  const float* g_slab;    // [n_t, N, H] cotangents of the outputs
+  float* lam;             // [N, H] running adjoint; result = dL/dy0
+  float* U;               // [N, H] scratch
+  float* S[8];            // scratch states: K1, K2, Y2, Y3, Y4, G4, G3, G2 (rk4) / YM, GM (midpoint)
+  float* part;            // [n_warps][H*H + H] per-warp dW / db contributions
+  float* dW;              // [H,H] out
+  float* db;              // [H] out
+  int64_t numel;
+};
+
+struct AdjP1 { const float* x; const float* t[4]; float c[4]; int nt; float scale; };
+struct AdjP2 { float* out; const float* add[5]; int na; };
+
+__device__ __forceinline__ float adj_gather_narrow(const GraphView& g, const float* __restrict__ x, int H, int64_t row,
+                                                   int lane, bool act) {
+  float s = 0.f;
+  const int start = g.rowptr[row], end = g.rowptr[row + 1];
+  for (int base = start; base < end; base += 32) {
+    int my_c = 0;
+    float my_v = 0.f;
+    if (base + lane < end) {
+      my_c = __ldg(g.col + base + lane);
+      my_v = __ldg(g.val + base + lane);
+    }
+    const int cnt = min(32, end - base);
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+      float xv[8], vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cj = __shfl_sync(0xffffffffu, my_c, (j0 + u) & 31);
+        vv[u] = __shfl_sync(0xffffffffu, my_v, (j0 + u) & 31);
+        xv[u] = (act && j0 + u < cnt) ? x[(int64_t)cj * H + lane] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j0 + u < cnt) s = fmaf(vv[u], xv[u], s);
+    }
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kStageThreads, 2) k_adjoint_small(const __grid_constant__ AdjArgs a,
+                                                                    const __grid_constant__ SmallArgs fw) {
+  extern __shared__ __align__(128) float zs[];  // [warps][64]: z row | gp row
+  __shared__ float s_wt[32 * 33];               // W^T[k][n]
+  __shared__ float s_w[32 * 33];                // W[o][i]
+  __shared__ EpiArgs s_e, s_run;
+  __shared__ AdjP1 s_p1;
+  __shared__ AdjP2 s_p2;
+  cg::grid_group grid = cg::this_grid();
+  const int H = a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool act = lane < H;
+  const bool no_graph = a.flags & NDCN_F_NO_GRAPH, no_control = a.flags & NDCN_F_NO_CONTROL;
+  if (!no_control) {
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+      const int o = i / H, k = i % H;
+      s_wt[k * 33 + o] = a.W[i];
+      s_w[o * 33 + k] = a.W[i];
+    }
+  }
+  __syncthreads();
+  const int64_t w0 = (int64_t)blockIdx.x * kWarpsPerCta + warp, wn = (int64_t)gridDim.x * kWarpsPerCta;
+  float* zr = zs + warp * 64;
+  float* gpr = zr + 32;
+  float dWacc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) dWacc[i] = 0.f;
+  float dbacc = 0.f;
+  uint32_t chunk_it = 0;
+
+  // P1 over all rows, parameters in s_p1
+  auto phase1 = [&]() {
+    const AdjP1 p = s_p1;
+    for (int64_t row = w0; row < a.n_rows; row += wn) {
+      float z = 0.f;
+      if (no_graph) { if (act) z = p.x[row * H + lane]; }
+      else z = adj_gather_narrow(a.g, p.x, H, row, lane, act);
+      float gk = 0.f;
+      if (act) {
+        for (int m = 0; m < p.nt; ++m) gk = fmaf(p.c[m], p.t[m][row * H + lane], gk);
+      }
+      if (act) zr[lane] = z;
+      __syncwarp();
+      float pre = z;
+      if (!no_control && act) {
+        float t = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) t = fmaf(zr[k], s_wt[k * 33 + lane], t);
+        pre = t + __ldg(a.bias + lane);
+      }
+      const float gp = (act && pre > 0.f) ? p.scale * gk : 0.f;
+      float u = gp;
+      if (!no_control) {
+        if (act) gpr[lane] = gp;
+        __syncwarp();
+        if (act) {
+          float t = 0.f;
+#pragma unroll 4
+          for (int o = 0; o < H; ++o) t = fmaf(gpr[o], s_w[o * 33 + lane], t);
+          u = t;
+          // dW[o = lane][i] += gp[o] z[i]
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < H) dWacc[i] = fmaf(gp, zr[i], dWacc[i]);
+          dbacc += gp;
+        }
+      }
+      if (act) a.U[row * H + lane] = u;
+      __syncwarp();
+    }
+  };
+  // P2 over all rows: out = sum of addends + Phi^T U
+  auto phase2 = [&]() {
+    const AdjP2 p = s_p2;
+    for (int64_t row = w0; row < a.n_rows; row += wn) {
+      float s = no_graph ? (act ? a.U[row * H + lane] : 0.f) : adj_gather_narrow(a.gt, a.U, H, row, lane, act);
+      if (act) {
+        for (int m = 0; m < p.na; ++m) s += p.add[m][row * H + lane];
+        p.out[row * H + lane] = s;
+      }
+    }
+  };
+#define ADJ_T0 if (threadIdx.x == 0)
+#define ADJ_SYNC() __syncthreads()
+#define ADJ_STAGE(src)                                                                    \
+  do {                                                                                    \
+    __syncthreads();                                                                      \
+    ADJ_T0 { s_run = s_e; s_run.partials = nullptr; }                                     \
+    __syncthreads();                                                                      \
+    small_stage<0, 0, false>(fw, src, s_run, zs, s_wt, chunk_it);                         \
+    grid.sync();                                                                          \
+  } while (0)
+
+  // lam = g_slab[n_t - 1]
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.numel; i += (int64_t)gridDim.x * blockDim.x)
+    a.lam[i] = a.g_slab[(int64_t)(a.n_t - 1) * a.numel + i];
+  grid.sync();
+
+  for (int i = a.n_t - 2; i >= 0; --i) {
+    const float* y = a.slab + (int64_t)i * a.numel;
+    const float* gi = a.g_slab + (int64_t)i * a.numel;
+    const float dt = a.dts[i];
+    if (a.method == NDCN_EULER) {  // y' = y + dt f(y)
+      ADJ_T0 { s_p1.x = y; s_p1.t[0] = a.lam; s_p1.c[0] = 1.f; s_p1.nt = 1; s_p1.scale = dt; }
+      ADJ_SYNC();
+      phase1();
+      grid.sync();
+      ADJ_T0 { s_p2.out = a.lam; s_p2.add[0] = a.lam; s_p2.add[1] = gi; s_p2.na = 2; }
+      ADJ_SYNC();
+      phase2();
+      grid.sync();
+    } else if (a.method == NDCN_MIDPOINT) {  // y' = y + dt f(ym), ym = y + dt/2 f(y)
+      float* YM = a.S[0];
+      float* GM = a.S[1];
+      ADJ_T0 {
+        small_blank(s_e);
+        s_e.dt_src = DT_HOST; s_e.dt_host = dt; s_e.y0 = spp(const_cast<float*>(y));
+        s_e.mode = EPI_LINCOMB; s_e.beta[0] = 0.5f; s_e.y_out = spp(YM);
+      }
+      ADJ_STAGE(spp(const_cast<float*>(y)));
+      ADJ_T0 { s_p1.x = YM; s_p1.t[0] = a.lam; s_p1.c[0] = 1.f; s_p1.nt = 1; s_p1.scale = dt; }
+      ADJ_SYNC();
+      phase1();
+      grid.sync();
+      ADJ_T0 { s_p2.out = GM; s_p2.na = 0; }
+      ADJ_SYNC();
+      phase2();
+      grid.sync();
+      ADJ_T0 { s_p1.x = y; s_p1.t[0] = GM; s_p1.c[0] = 1.f; s_p1.nt = 1; s_p1.scale = dt * 0.5f; }
+      ADJ_SYNC();
+      phase1();
+      grid.sync();
+      ADJ_T0 { s_p2.out = a.lam; s_p2.add[0] = a.lam; s_p2.add[1] = GM; s_p2.add[2] = gi; s_p2.na = 3; }
+      ADJ_SYNC();
+      phase2();
+      grid.sync();
+    } else {  // rk4 = 3/8 rule, rk_common.py:72-78
+      float *K1 = a.S[0], *K2 = a.S[1], *Y2 = a.S[2], *Y3 = a.S[3], *Y4 = a.S[4], *G4 = a.S[5], *G3 = a.S[6], *G2 = a.S[7];
+      ADJ_T0 {
+        small_blank(s_e);
+        s_e.dt_src = DT_HOST; s_e.dt_host = dt; s_e.y0 = spp(const_cast<float*>(y));
+        s_e.mode = EPI_RK4_1; s_e.k_out = spp(K1); s_e.y_out = spp(Y2);
+      }
+      ADJ_STAGE(spp(const_cast<float*>(y)));
+      ADJ_T0 { s_e.mode = EPI_RK4_2; s_e.k_out = spp(K2); s_e.kprev[0] = spp(K1); s_e.y_out = spp(Y3); }
+      ADJ_STAGE(spp(Y2));
+      ADJ_T0 { s_e.mode = EPI_RK4_3; s_e.k_out = spp(nullptr); s_e.kprev[1] = spp(K2); s_e.y_out = spp(Y4); }
+      ADJ_STAGE(spp(Y3));
+      // g4 = dL/dy4 through k4:  y' = y + (k1 + 3 k2 + 3 k3 + k4) dt/8
+      ADJ_T0 { s_p1.x = Y4; s_p1.t[0] = a.lam; s_p1.c[0] = 1.f; s_p1.nt = 1; s_p1.scale = dt / 8.f; }
+      ADJ_SYNC(); phase1(); grid.sync();
+      ADJ_T0 { s_p2.out = G4; s_p2.na = 0; }
+      ADJ_SYNC(); phase2(); grid.sync();
+      // k3 feeds y' (3 dt/8) and y4 (dt)
+      ADJ_T0 { s_p1.x = Y3; s_p1.t[0] = a.lam; s_p1.c[0] = 3.f * dt / 8.f; s_p1.t[1] = G4; s_p1.c[1] = dt; s_p1.nt = 2; s_p1.scale = 1.f; }
+      ADJ_SYNC(); phase1(); grid.sync();
+      ADJ_T0 { s_p2.out = G3; s_p2.na = 0; }
+      ADJ_SYNC(); phase2(); grid.sync();
+      // k2 feeds y' (3 dt/8), y4 (-dt) and y3 (dt)
+      ADJ_T0 {
+        s_p1.x = Y2; s_p1.t[0] = a.lam; s_p1.c[0] = 3.f * dt / 8.f; s_p1.t[1] = G4; s_p1.c[1] = -dt; s_p1.t[2] = G3; s_p1.c[2] = dt;
+        s_p1.nt = 3; s_p1.scale = 1.f;
+      }
+      ADJ_SYNC(); phase1(); grid.sync();
+      ADJ_T0 { s_p2.out = G2; s_p2.na = 0; }
+      ADJ_SYNC(); phase2(); grid.sync();
+      // k1 feeds y' (dt/8), y4 (dt), y3 (-dt/3) and y2 (dt/3)
+      ADJ_T0 {
+        s_p1.x = y; s_p1.t[0] = a.lam; s_p1.c[0] = dt / 8.f; s_p1.t[1] = G4; s_p1.c[1] = dt; s_p1.t[2] = G3; s_p1.c[2] = -dt / 3.f;
+        s_p1.t[3] = G2; s_p1.c[3] = dt / 3.f; s_p1.nt = 4; s_p1.scale = 1.f;
+      }
+      ADJ_SYNC(); phase1(); grid.sync();
+      ADJ_T0 { s_p2.out = a.lam; s_p2.add[0] = a.lam; s_p2.add[1] = G4; s_p2.add[2] = G3; s_p2.add[3] = G2; s_p2.add[4] = gi; s_p2.na = 5; }
+      ADJ_SYNC(); phase2(); grid.sync();
+    }
+  }
+  // parameter gradients: every warp parks its contribution, then a fixed-order sum over the warps
+  if (!no_control) {
+    float* mine = a.part + (size_t)w0 * (H * H + H);
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < H) mine[lane * H + i] = dWacc[i];
+      mine[H * H + lane] = dbacc;
+    }
+    grid.sync();
+    const int total = H * H + H;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+      float sum = 0.f;
+      for (int64_t w = 0; w < wn; ++w) sum += a.part[(size_t)w * total + j];
+      if (j < H * H) a.dW[j] = sum;
+      else a.db[j - H * H] = sum;
+    }
+  }
+#undef ADJ_T0
+#undef ADJ_SYNC
+#undef ADJ_STAGE
+}
 
 }  // namespace ndcn

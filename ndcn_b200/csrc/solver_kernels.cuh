@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(kStageThreads) k_copy_slices(const float* __re
     const int64_t off = i * 4;
     const int64_t row = off >> h_log2;
     const int col = (int)(off & (((int64_t)1 << h_log2) - 1));
-    float* p = feat->xcs[col >> hc_log2] + (((int64_t)row0 + row) << hc_log2) + (col & ((1 << hc_log2) - 1));
+    const int cs = col & ((1 << hc_log2) - 1);
+    float* p = feat->xcs[col >> hc_log2];
+    if (feat->slab) p += (((int64_t)(cs >> 4) * feat->n_total + row0 + row) << 4) + (cs & 15);
+    else p += (((int64_t)row0 + row) << hc_log2) + cs;
     *reinterpret_cast<float4*>(p) = v;
   }
 }

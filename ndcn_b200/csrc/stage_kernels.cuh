@@ -464,15 +464,11 @@ __device__ __forceinline__ float dyn_local(const float (&p)[8], float xi, float 
 
 // [N,1] state: LPR lanes cooperate on one row (degree ~10), shuffle-reduce, then the
 // results are compacted so that the epilogue's loads/stores are contiguous.
+// the 32 / LPR rows starting at warp_global * (32 / LPR), by one warp
 template <int KIND, int LPR>
-__global__ void __launch_bounds__(kStageThreads) k_stage_dyn1(DynArgs a, EpiArgs e) {
-  EpiCtx c;
-  if (!epi_resolve(e, c)) return;
-  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
-  const float* __restrict__ x = sel(a.x, par);
+__device__ __forceinline__ void dyn1_warp_rows(const DynArgs& a, const float* __restrict__ x, int64_t warp_global,
+                                               int lane, const EpiCtx& c, double& err_acc) {
   constexpr int RPWARP = 32 / LPR;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t row_base = warp_global * RPWARP;
   const int64_t row = row_base + lane / LPR;
   const int sub = lane % LPR;
@@ -490,12 +486,21 @@ __global__ void __launch_bounds__(kStageThreads) k_stage_dyn1(DynArgs a, EpiArgs
   float kval = dyn_local<KIND>(a.p, xi, s);
   // lane i < RPWARP takes the result of row row_base + i (held by lane i*LPR)
   kval = __shfl_sync(0xffffffffu, kval, (lane * LPR) & 31);
-  double err_acc = 0.0;
   const int64_t my_row = row_base + lane;
   if (lane < RPWARP && my_row < a.g.n_rows) {
     float kv[1] = {kval};
     epi_apply<1>(c, my_row, kv, err_acc);
   }
+}
+
+template <int KIND, int LPR>
+__global__ void __launch_bounds__(kStageThreads) k_stage_dyn1(DynArgs a, EpiArgs e) {
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  const float* __restrict__ x = sel(a.x, par);
+  double err_acc = 0.0;
+  dyn1_warp_rows<KIND, LPR>(a, x, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31, c, err_acc);
   epi_finish_block(e, err_acc);
 }
 
@@ -514,24 +519,6 @@ __device__ __forceinline__ void dynv_row(const DynArgs& a, const float* __restri
     }
     float kv[1] = {dyn_local<KIND>(a.p, xi, s)};
     epi_apply<1>(c, row * d + col, kv, err_acc);
-  }
-}
-
-// [N,1] state, one warp per row: the lanes stride over the row's entries, shuffle-reduce, lane 0 finishes
-// (the persistent small-graph solver's flavour; k_stage_dyn1 packs several rows into a warp instead)
-template <int KIND>
-__device__ __forceinline__ void dyn1_row_warp(const DynArgs& a, const float* __restrict__ x, int64_t row, int lane,
-                                              const EpiCtx& c, double& err_acc) {
-  const float xi = x[row];
-  const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
-  float s = 0.f;
-  for (int j = start + lane; j < end; j += 32)
-    s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, x[__ldg(a.g.col + j)], true));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s = fadd(s, __shfl_xor_sync(0xffffffffu, s, o));
-  if (lane == 0) {
-    float kv[1] = {dyn_local<KIND>(a.p, xi, s)};
-    epi_apply<1>(c, row, kv, err_acc);
   }
 }
 

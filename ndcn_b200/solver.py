@@ -90,28 +90,38 @@ class SolveInfo:
 
 last_solve_info: Optional[SolveInfo] = None
 
-_PREPARED: Dict[tuple, torch.Tensor] = {}
+_PREPARED: list = []  # [(weight tensor, version, prepared buffer)], most recent last
+
+
+def clear_prepared() -> None:
+    """Forget the derived weight forms (call after mutating a weight through ``.data``, which bumps no version)."""
+    _PREPARED.clear()
 
 
 def prepared_weights(W_param: torch.Tensor, W32: torch.Tensor) -> torch.Tensor:
     """Device buffer with the derived forms of an ``nn.Linear`` weight the kernels consume (``ndcn_prepare_weights_f32``),
-    cached on (storage, in-place version): an optimiser step bumps the version, so a training iteration prepares
-    once and its dozens of RHS evaluations / vjps reuse the buffer."""
-    key = (W_param.data_ptr(), W_param._version, tuple(W_param.shape), str(W_param.device))
-    buf = _PREPARED.get(key)
-    if buf is None:
-        if len(_PREPARED) >= 8:
-            _PREPARED.pop(next(iter(_PREPARED)))
-        lib = _ffi.lib()
-        H = int(W32.shape[0])
-        nbytes = int(lib.ndcn_prepared_weights_bytes(H))
-        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=W32.device)
-        off = (-raw.data_ptr()) % 1024
-        buf = raw[off:off + nbytes]
-        with torch.cuda.device(W32.device):
-            _ffi.check(lib.ndcn_prepare_weights_f32(W32.data_ptr(), H, buf.data_ptr(), current_stream_ptr(W32.device)),
-                       "ndcn_prepare_weights_f32")
-        _PREPARED[key] = buf
+    cached per (tensor object, in-place version): an optimiser step bumps the version, so a training iteration
+    prepares once and its dozens of RHS evaluations / vjps reuse the buffer.  The cache keeps the weight tensor
+    alive, so a recycled ``data_ptr`` can never alias an entry."""
+    for i in range(len(_PREPARED) - 1, -1, -1):
+        w, ver, buf = _PREPARED[i]
+        if w is W_param:
+            if ver == W_param._version:
+                return buf
+            del _PREPARED[i]
+            break
+    if len(_PREPARED) >= 8:
+        del _PREPARED[0]
+    lib = _ffi.lib()
+    H = int(W32.shape[0])
+    nbytes = int(lib.ndcn_prepared_weights_bytes(H))
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=W32.device)
+    off = (-raw.data_ptr()) % 1024
+    buf = raw[off:off + nbytes]
+    with torch.cuda.device(W32.device):
+        _ffi.check(lib.ndcn_prepare_weights_f32(W32.data_ptr(), H, buf.data_ptr(), current_stream_ptr(W32.device)),
+                   "ndcn_prepare_weights_f32")
+    _PREPARED.append((W_param, W_param._version, buf))
     return buf
 
 
@@ -148,6 +158,7 @@ _SOLVERS: Dict[tuple, tuple] = {}
 
 
 def release_workspaces() -> None:
+    _PREPARED.clear()
     for handle, _g in _SOLVERS.values():
         _ffi.lib().ndcn_solver_destroy(handle)
     _SOLVERS.clear()
@@ -158,8 +169,12 @@ def current_stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def rhs_eval(graph: CsrGraph, spec: RhsSpec, x: torch.Tensor) -> torch.Tensor:
-    """One evaluation f(x) on the GPU (ODEFunc.forward / *Dynamics.forward)."""
+def rhs_eval(graph: CsrGraph, spec: RhsSpec, x: torch.Tensor, cache_weights: bool = False) -> torch.Tensor:
+    """One evaluation f(x) on the GPU (ODEFunc.forward / *Dynamics.forward).
+
+    ``cache_weights``: reuse the derived weight forms across calls while the weight's autograd version is unchanged
+    (the training path, where weights change through optimiser steps only); off by default because a mutation
+    through ``.data`` bumps no version."""
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
     x = x.contiguous()
     if x.shape[0] != graph.n_cols or x.shape[1] != spec.H:
@@ -167,7 +182,7 @@ def rhs_eval(graph: CsrGraph, spec: RhsSpec, x: torch.Tensor) -> torch.Tensor:
                          (tuple(x.shape), graph.n_cols, spec.H))
     out = torch.empty((graph.n_rows, spec.H), dtype=torch.float32, device=x.device)
     keep: list = []
-    desc = spec.to_c(keep, prepare=True)
+    desc = spec.to_c(keep, prepare=cache_weights)
     with torch.cuda.device(x.device):
         rc = _ffi.lib().ndcn_rhs_eval_f32(graph.handle, C.byref(desc), x.data_ptr(), out.data_ptr(),
                                           current_stream_ptr(x.device))

@@ -150,3 +150,55 @@ def test_errors_and_eligibility(golden):
     with pytest.raises(ValueError):
         nb.odeint_fused(big, spec, x, torch.tensor([0.0, 0.1]), method="euler", small=True)
     nb.odeint_fused(big, spec, x, torch.tensor([0.0, 0.1]), method="euler")
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+@pytest.mark.parametrize("flags", ["full", "no_graph", "no_control"])
+def test_persistent_adjoint_matches_step_by_step_backward(method, flags):
+    """ndcn_fixed_grid_adjoint_small_f32: the backward pass of a fixed-grid solve at H <= 32 (the dynamics scripts'
+    training loop, heat_dynamics.py:317-334) as ONE cooperative launch, against the launch-per-vjp backward and
+    CPU autograd through the oracle."""
+    import ndcn_b200 as nb
+    from ndcn_b200 import autograd_solver
+    n, H = 500, 20
+    rs = np.random.RandomState(3)
+    r, c = rs.randint(0, n, 4 * n), rs.randint(0, n, 4 * n)
+    k = r != c
+    A = torch.zeros(n, n)
+    A[r[k], c[k]] = 1.0
+    A = A / A.sum(1, keepdim=True).clamp(min=1.0)  # non-symmetric: Phi^T is a different matrix
+    kw = dict(no_graph=flags == "no_graph", no_control=flags == "no_control")
+    torch.manual_seed(1)
+    func = nb.ODEFunc(H, A.to_sparse(), **kw).cuda()
+    x0 = torch.randn(n, H)
+    t = torch.tensor([0.0, 0.2, 0.35, 0.7, 1.0])
+    wts = torch.randn(5, n, H) / (n * H) ** 0.5
+
+    def grads(persistent):
+        autograd_solver.FusedFixedGridFn.persistent_backward = persistent
+        try:
+            func.zero_grad(set_to_none=True)
+            xg = x0.clone().cuda().requires_grad_()
+            out = nb.odeint(func, xg, t.cuda(), method=method)
+            (out * wts.cuda()).sum().backward()
+            gw = func.wt.weight.grad.clone() if flags != "no_control" else None
+            gb = func.wt.bias.grad.clone() if flags != "no_control" else None
+            return xg.grad.clone(), gw, gb
+        finally:
+            autograd_solver.FusedFixedGridFn.persistent_backward = True
+
+    a, b = grads(True), grads(False)
+
+    def rel(u, v):
+        return float((u - v).norm() / v.norm().clamp(min=1e-30))
+
+    assert rel(a[0], b[0]) < 1e-5
+    if flags != "no_control":
+        assert rel(a[1], b[1]) < 1e-5 and rel(a[2], b[2]) < 1e-5
+    W = func.wt.weight.detach().cpu().clone().requires_grad_()
+    bb = func.wt.bias.detach().cpu().clone().requires_grad_()
+    xr = x0.clone().requires_grad_()
+    (O.odeint(lambda tt, x: O.rhs_ndcn(A, W, bb, x, **kw), xr, t, method=method) * wts).sum().backward()
+    assert rel(a[0].cpu(), xr.grad) < 1e-4
+    if flags != "no_control":
+        assert rel(a[1].cpu(), W.grad) < 1e-4 and rel(a[2].cpu(), bb.grad) < 1e-4
