@@ -720,6 +720,23 @@ def main_ours(args):
             line["config"]["parallelism"] = "1-D node-row partition x%d, NCCL halo exchange before every RHS eval" % world
         line["partition"] = part.describe()
         line["partition"]["exchange_bytes_per_rhs_and_rank"] = vols
+        # NVLink side of the roofline: bytes THIS rank stores into peer memory per RHS
+        # evaluation over the device time of the kernels that issue those stores (stage kernels + slice gather);
+        # peak = the measured peer-copy bandwidth per direction and GPU (B200_PROFILING.md: 770 GB/s, nominal 900)
+        sent = None
+        if peers is not None and scheme == "fpush":
+            sent = 2 * graph.n_rows * H * 4 * (world - 1) // world      # y slices out + z blocks out
+        elif peers is not None:
+            sent = graph.n_rows * H * 4 * (world - 1)                     # whole rows to every peer
+        elif vols is not None:
+            sent = vols.get("feature") if z_block_cols else vols.get("halo")
+        if sent:
+            busy_ms = (stage_ms + gather_ms) / max(stage_n, 1)
+            line["nvlink"] = {"sent_bytes_per_rhs_and_rank": int(sent), "unit": "GB/s",
+                              "achieved": sent / (busy_ms * 1e-3) / 1e9 if busy_ms > 0 else None, "peak": 770.0,
+                              "frac": sent / (busy_ms * 1e-3) / 1e9 / 770.0 if busy_ms > 0 else None,
+                              "over": "device time of one RHS evaluation on rank 0 (stage kernel + gather), %.3f ms" % busy_ms,
+                              "peak_source": "measured peer copy per direction (B200_PROFILING.md)"}
         # per-rank device time by kernel class (ms per step, CUDA events of the timed solve): where the ranks differ
         # -- `exchange` is the time inside the barrier kernels, i.e. mostly waiting for the slowest rank
         try:

@@ -375,9 +375,13 @@ k_stage_gather_v2(NdcnArgs a, int H, int n_blocks, int n_long, const int32_t* __
 constexpr int kSlabRows = 128;
 constexpr int kSlabCap = 2048;
 
+// `rb_shift`: the grid walks the row blocks starting at this one (wrapping around).  Every rank of the feature-sharded
+// push gathers ALL rows and stores z to the rows' owners in the same order; a per-rank start (rank q at its own block)
+// keeps the ranks on different owners at any moment.  Measured: no gain (see the caller), default 0.
 __global__ void __launch_bounds__(kStageThreads, 6) k_gather_slab(GraphView g, const float* __restrict__ x,
                                                                   int64_t n_src, int n_rb, int n_long,
-                                                                  const int32_t* __restrict__ long_rows, EpiArgs e) {
+                                                                  const int32_t* __restrict__ long_rows, int rb_shift,
+                                                                  EpiArgs e) {
   __shared__ __align__(16) float s_part[(kStageThreads / 4) * 16];
   __shared__ int s_col[kSlabCap];
   __shared__ float s_val[kSlabCap];
@@ -387,7 +391,11 @@ __global__ void __launch_bounds__(kStageThreads, 6) k_gather_slab(GraphView g, c
   constexpr int G = kStageThreads / 4;
   const int bpc = n_rb + n_long;
   const int slab = blockIdx.x / bpc;
-  const int b = blockIdx.x - slab * bpc;
+  int b = blockIdx.x - slab * bpc;
+  if (b < n_rb) {
+    b += rb_shift;
+    if (b >= n_rb) b -= n_rb;
+  }
   const int sub = threadIdx.x & 3;
   const int gidx = threadIdx.x >> 2;
   const float* __restrict__ xs = x + (size_t)slab * n_src * 16 + sub * 4;

@@ -1285,7 +1285,14 @@ struct Driver : StageTimer {
         const int n_rb = (int)((fg->v.n_rows + kSlabRows - 1) / kSlabRows);
         const int64_t grid = (int64_t)(sv->feat_hc / 16) * (n_rb + fg->n_long);
         sv->launches += 1;
-        k_gather_slab<<<(unsigned)grid, kStageThreads, 0, st>>>(fg->v, sv->xcs_self, fg->v.n_cols, n_rb, fg->n_long, fg->long_rows, se);
+        // NDCN_FEAT_ROTATE=1: every rank starts the walk at its own row block, so that at any moment the ranks store z
+        // to different owners.  Measured on 8 / 4 B200s (profiles/README.md): 5.47 / 9.06 ms per step against
+        // 5.33 / 8.76 ms with the common start -- the hub-heavy first block desynchronises the ranks either way -- so off
+        int rb_shift = 0;
+        if (const char* v = std::getenv("NDCN_FEAT_ROTATE"))
+          if (std::atoi(v)) rb_shift = (int)((int64_t)sv->feat_bounds[sv->feat_rank] / kSlabRows);
+        k_gather_slab<<<(unsigned)grid, kStageThreads, 0, st>>>(fg->v, sv->xcs_self, fg->v.n_cols, n_rb, fg->n_long, fg->long_rows,
+                                                                rb_shift % std::max(n_rb, 1), se);
         rcg = (int)cudaGetLastError();
       } else {
         rcg = launch_stage(bg, pp(sv->xcs_self), se, nullptr, st);
@@ -1782,7 +1789,16 @@ static int run_small(Driver& d, const float* y0, const double* t, int n_t, float
   int grid = 0, rc = 0;
   sv->launches += 1;
   d.t_begin(NDCN_K_STAGE);
-  if (tiled) {
+  // one CTA, element-parallel, z in shared memory: the 400-node grid at H = 20, every small [N,d] dynamics state
+  static const bool tiny_on = [] { const char* v = std::getenv("NDCN_TINY"); return !v || std::atoi(v) != 0; }();
+  const bool tiny = tiny_on && sv->numel <= kTinyMaxNumel && (sv->rhs.kind != NDCN_RHS_NDCN || sv->H <= 32);
+  if (tiny) {
+    const size_t smem = sv->rhs.kind == NDCN_RHS_NDCN ? sizeof(float) * (size_t)sv->numel : 16;
+    SmallArgs copy = a;
+    grid = 1;
+    k_solve_small<0, 0, false, true><<<1, kTinyThreads, smem, st>>>(copy);
+    rc = (int)cudaGetLastError();
+  } else if (tiled) {
     switch (sv->H) {
       case 256: rc = launch_small<4, 2, true>(a, GemmSmem<4, 2>::total, sv->sm_count, want, &grid, st); break;
       case 128: rc = launch_small<4, 1, true>(a, GemmSmem<4, 1>::total, sv->sm_count, want, &grid, st); break;
@@ -1977,7 +1993,9 @@ extern "C" int ndcn_solver_set_feature_peers(ndcn_solver_t* sv, const ndcn_graph
   for (int r = 0; r <= 8; ++r) t.bounds[r] = (int)cfg->row_bounds[r <= P ? r : P];
   t.world = P;
   t.n_total = (int)cfg->row_bounds[P];
-  sv->feat_slab = true;
+  // slice rows of 128 / 256 bytes (Hc = 32 / 64) are what the slab layout fixes; from Hc = 128 on the warp-per-row
+  // gather on row-major slices is faster (measured at 2 GPUs: 1.29 ms vs 1.53 ms per gather at Hc = 128)
+  sv->feat_slab = hc <= 64;
   if (const char* v = std::getenv("NDCN_FEAT_SLAB")) sv->feat_slab = std::atoi(v) != 0;
   t.slab = sv->feat_slab ? 1 : 0;
   t.nl_uniform = (int)(cfg->row_bounds[1] - cfg->row_bounds[0]);

@@ -228,6 +228,73 @@ __device__ __noinline__ void small_stage(const SmallArgs& a, PtrPair src, const 
   epi_finish_block(e, err_acc);
 }
 
+// TINY: the whole problem on ONE CTA (<= 8192 state elements: the 400-node grid of the dynamics scripts at H=20, every
+// [N,1] ground-truth state).  Element-parallel instead of row-per-warp: thread e owns element (r, c) = (e / H, e % H) --
+// a few hundred rows cannot feed 16 warps row by row, but 8000 elements feed 512 threads -- with z = Phi x parked in
+// shared memory between the gather and the Linear.  Block barriers replace the grid barriers; everything the CTA
+// touches stays in its SM's L1.  Same accumulation orders as the row kernels (CSR order; k = 0..H-1): same bits.
+__device__ __noinline__ void tiny_stage(const SmallArgs& a, PtrPair src, const EpiArgs& e, float* zs, const float* wt_s) {
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  const float* __restrict__ x = sel(src, par);
+  double err_acc = 0.0;
+  const int H = a.H;
+  const int numel = (int)a.numel;
+  if (a.kind == NDCN_RHS_NDCN) {
+    const bool no_graph = a.flags & NDCN_F_NO_GRAPH, no_control = a.flags & NDCN_F_NO_CONTROL;
+    const bool relu = !(a.flags & NDCN_F_NO_RELU);
+    for (int el = threadIdx.x; el < numel; el += blockDim.x) {
+      const int r = el / H, cc = el - r * H;
+      float s = 0.f;
+      if (no_graph) {
+        s = x[el];
+      } else {
+        const int start = a.g.rowptr[r], end = a.g.rowptr[r + 1];
+        for (int j = start; j < end; ++j) s = fmaf(__ldg(a.g.val + j), x[__ldg(a.g.col + j) * H + cc], s);
+      }
+      zs[el] = s;
+    }
+    __syncthreads();
+    for (int el = threadIdx.x; el < numel; el += blockDim.x) {
+      const int r = el / H, cc = el - r * H;
+      float kv[1];
+      if (no_control) {
+        kv[0] = zs[el];
+      } else {
+        float t = 0.f;
+        const float* zr = zs + r * H;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) t = fmaf(zr[k], wt_s[k * 33 + cc], t);
+        kv[0] = t + __ldg(a.bias + cc);
+      }
+      if (relu) kv[0] = fmaxf(kv[0], 0.f);
+      epi_apply<1>(c, el, kv, err_acc);
+    }
+  } else {
+    const int d = H;
+    for (int el = threadIdx.x; el < numel; el += blockDim.x) {
+      const int r = el / d, cc = el - r * d;
+      const float xi = x[el];
+      const int start = a.g.rowptr[r], end = a.g.rowptr[r + 1];
+      float s = 0.f;
+      for (int j = start; j < end; ++j) {
+        const float xj = x[__ldg(a.g.col + j) * d + cc];
+        const float av = __ldg(a.g.val + j);
+        if (a.kind == NDCN_RHS_HEAT) s = fadd(s, dyn_neighbour<NDCN_RHS_HEAT>(a.p, av, xi, xj, d == 1));
+        else if (a.kind == NDCN_RHS_GENE) s = fadd(s, dyn_neighbour<NDCN_RHS_GENE>(a.p, av, xi, xj, d == 1));
+        else s = fadd(s, dyn_neighbour<NDCN_RHS_MUTUAL>(a.p, av, xi, xj, d == 1));
+      }
+      float kv[1];
+      if (a.kind == NDCN_RHS_HEAT) kv[0] = dyn_local<NDCN_RHS_HEAT>(a.p, xi, s);
+      else if (a.kind == NDCN_RHS_GENE) kv[0] = dyn_local<NDCN_RHS_GENE>(a.p, xi, s);
+      else kv[0] = dyn_local<NDCN_RHS_MUTUAL>(a.p, xi, s);
+      epi_apply<1>(c, el, kv, err_acc);
+    }
+  }
+  epi_finish_block(e, err_acc);
+}
+
 __device__ __noinline__ void small_epi_only(const SmallArgs& a, PtrPair k_in, const EpiArgs& e) {
   EpiCtx c;
   if (!epi_resolve(e, c)) return;
@@ -284,12 +351,16 @@ __device__ __forceinline__ double small_sum_partials(const double* partials, int
     __syncthreads();                                \
   } while (0)
 
-template <int VW, int NCH, bool CONTROL>
-__global__ void __launch_bounds__(kStageThreads, (VW > 0 && CONTROL) ? 1 : 2)
+constexpr int kTinyThreads = 512;
+constexpr int kTinyMaxNumel = 8192;  // z = Phi x of the whole state in shared memory (32 KB)
+
+template <int VW, int NCH, bool CONTROL, bool TINY = false>
+__global__ void __launch_bounds__(TINY ? kTinyThreads : kStageThreads, (TINY || (VW > 0 && CONTROL)) ? 1 : 2)
 k_solve_small(const __grid_constant__ SmallArgs a) {
-  // VW == 0: [warps][max(H, 32)] scratch rows of the row-per-warp right-hand side; tiled GEMM: GemmSmem<VW, NCH>
+  // VW == 0: [warps][max(H, 32)] scratch rows of the row-per-warp right-hand side; tiled GEMM: GemmSmem<VW, NCH>;
+  // TINY: z = Phi x of the whole state, [numel]
   extern __shared__ __align__(128) float zs[];
-  __shared__ double s_tmp[kStageThreads];
+  __shared__ double s_tmp[TINY ? kTinyThreads : kStageThreads];
   __shared__ float s_xs[kEmitMaxPerLaunch * 4];
   __shared__ float s_wt[32 * 33];  // W^T of a narrow Linear (H <= 32), padded rows
   __shared__ EpiArgs s_e, s_run;
@@ -304,14 +375,23 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
     }
   }
   __syncthreads();
-#define NDCN_STAGE(src) small_stage<VW, NCH, CONTROL>(a, src, s_run, zs, s_wt, chunk_it)
+#define NDCN_STAGE(src)                                                             \
+  do {                                                                              \
+    if constexpr (TINY) tiny_stage(a, src, s_run, zs, s_wt);                        \
+    else small_stage<VW, NCH, CONTROL>(a, src, s_run, zs, s_wt, chunk_it);          \
+  } while (0)
+#define NDCN_BAR()                                  \
+  do {                                              \
+    if constexpr (TINY) __syncthreads();            \
+    else grid.sync();                               \
+  } while (0)
 
   if (a.method != NDCN_DOPRI5) {
     // ---------------- fixed grid: euler / midpoint / rk4 (3/8 rule), solvers.py:79-99 ----------------
     float* cur = a.in_slab ? a.out : a.Y[0];
     small_copy(a.y0, cur, a.numel);
     if (!a.in_slab && !a.terminal) small_put_state(a, 0, a.y0);
-    grid.sync();
+    NDCN_BAR();
     for (int i = 0; i + 1 < a.n_t; ++i) {
       float* nxt = a.in_slab ? a.out + (int64_t)(i + 1) * a.numel : a.Y[(i + 1) & 1];
       NDCN_T0 {
@@ -324,33 +404,33 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
         NDCN_T0 { s_e.mode = EPI_LINCOMB; s_e.beta[0] = 1.0f; s_e.y_out = spp(nxt); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(cur));
-        grid.sync();
+        NDCN_BAR();
       } else if (a.method == NDCN_MIDPOINT) {  // fixed_grid.py:17-20
         NDCN_T0 { s_e.mode = EPI_LINCOMB; s_e.beta[0] = 0.5f; s_e.y_out = spp(a.YS[0]); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(cur));
-        grid.sync();
+        NDCN_BAR();
         NDCN_T0 { s_e.beta[0] = 1.0f; s_e.y_out = spp(nxt); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(a.YS[0]));
-        grid.sync();
+        NDCN_BAR();
       } else {  // rk_common.py:72-78
         NDCN_T0 { s_e.mode = EPI_RK4_1; s_e.k_out = spp(a.K[0]); s_e.y_out = spp(a.YS[0]); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(cur));
-        grid.sync();
+        NDCN_BAR();
         NDCN_T0 { s_e.mode = EPI_RK4_2; s_e.k_out = spp(a.K[1]); s_e.kprev[0] = spp(a.K[0]); s_e.y_out = spp(a.YS[1]); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(a.YS[0]));
-        grid.sync();
+        NDCN_BAR();
         NDCN_T0 { s_e.mode = EPI_RK4_3; s_e.k_out = spp(a.K[2]); s_e.kprev[1] = spp(a.K[1]); s_e.y_out = spp(a.YS[0]); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(a.YS[1]));
-        grid.sync();
+        NDCN_BAR();
         NDCN_T0 { s_e.mode = EPI_RK4_4; s_e.k_out = spp(nullptr); s_e.kprev[2] = spp(a.K[2]); s_e.y_out = spp(nxt); }
         NDCN_PUBLISH();
         NDCN_STAGE(spp(a.YS[0]));
-        grid.sync();
+        NDCN_BAR();
       }
       // the new state goes to its output slot while the next step already reads it (nobody writes `nxt` again
       // before the grid barrier that ends the next step)
@@ -368,20 +448,20 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
   if (!a.terminal) small_put_state(a, 0, a.y0);
   NDCN_T0 { small_blank(s_e); s_e.k_out = spp(a.KF[0]); }  // f0 = func(t0, y0)     dopri5.py:78
   NDCN_PUBLISH();
-  grid.sync();
+  NDCN_BAR();
   NDCN_STAGE(spp(a.Y[0]));
-  grid.sync();
+  NDCN_BAR();
   if (!a.forced && !a.given_first) {
     // _select_initial_step(order=4)     dopri5.py:80, misc.py:84-143
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     init_norms_block(a.Y[0], a.KF[0], nullptr, a.numel, a.rtol, a.atol, 0, a.partials, tid, stride);
-    grid.sync();
+    NDCN_BAR();
     if (blockIdx.x == 0) {
       const double s0 = small_sum_partials(a.partials, gridDim.x, 2, 0, s_tmp);
       const double s1 = small_sum_partials(a.partials, gridDim.x, 2, 1, s_tmp);
       if (threadIdx.x == 0) { init_scalar_decide(*ctrl, s0, s1, 0, a.t_first); __threadfence(); }
     }
-    grid.sync();
+    NDCN_BAR();
     NDCN_T0 {
       small_blank(s_e);
       s_e.ctrl = ctrl;
@@ -393,18 +473,18 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
     }
     NDCN_PUBLISH();
     small_epi_only(a, spp(a.KF[0]), s_run);  // y0 + h0*f0
-    grid.sync();
+    NDCN_BAR();
     NDCN_T0 { small_blank(s_e); s_e.k_out = spp(a.K[0]); }
     NDCN_PUBLISH();
     NDCN_STAGE(spp(a.YS[0]));
-    grid.sync();
+    NDCN_BAR();
     init_norms_block(a.Y[0], a.KF[0], a.K[0], a.numel, a.rtol, a.atol, 1, a.partials, tid, stride);
-    grid.sync();
+    NDCN_BAR();
     if (blockIdx.x == 0) {
       const double s0 = small_sum_partials(a.partials, gridDim.x, 2, 0, s_tmp);
       if (threadIdx.x == 0) { init_scalar_decide(*ctrl, s0, 0.0, 1, a.t_first); __threadfence(); }
     }
-    grid.sync();
+    NDCN_BAR();
   }
 
   EmitArgs em;
@@ -442,7 +522,7 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
     }
     NDCN_PUBLISH();
     small_epi_only(a, KFcur, s_run);
-    grid.sync();
+    NDCN_BAR();
     NDCN_T0 { s_e.check_finite = 0; s_e.kprev[0] = KFcur; }
     for (int s = 1; s <= 5; ++s) {
       NDCN_T0 {
@@ -459,7 +539,7 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
       }
       NDCN_PUBLISH();
       NDCN_STAGE(spp(a.YS[(s - 1) & 1]));
-      grid.sync();
+      NDCN_BAR();
     }
     // stage 6: k7 = f(y1) + error estimate
     NDCN_T0 {
@@ -484,7 +564,7 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
     }
     NDCN_PUBLISH();
     NDCN_STAGE(Yoth);
-    grid.sync();
+    NDCN_BAR();
     // accept / reject + next step size: block 0 (k_controller's arithmetic)
     if (blockIdx.x == 0) {
       if (((volatile Ctrl*)ctrl)->status != 0) {  // non-finite state flagged by the pre-stage
@@ -495,13 +575,14 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
       }
       __threadfence();
     }
-    grid.sync();
+    NDCN_BAR();
     // dense output of the step just accepted, for the requested times inside it; reads y0/y1/k_j only, the next
     // attempt's pre-stage writes YS[0] only: no barrier needed in between
     if (a.dec_C > 0) emit_decode_range(em, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5);
     else emit_range(em, a.vec, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, s_xs);
   }
 #undef NDCN_STAGE
+#undef NDCN_BAR
 }
 #undef NDCN_T0
 #undef NDCN_PUBLISH

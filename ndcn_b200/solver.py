@@ -5,7 +5,9 @@ every arithmetic operation of the path happens inside libndcn_b200.so.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Optional, Sequence, Tuple
 
@@ -139,12 +141,17 @@ def weight_grads(gp: torch.Tensor, z: torch.Tensor, dW: torch.Tensor, db: Option
     _ffi.check(rc, "ndcn_weight_grads_f32")
 
 _WORKSPACES: Dict[Tuple[str, int], torch.Tensor] = {}
+# One solve at a time per process: the workspace, the solver-handle cache and ``last_solve_info`` are module state,
+# and a handle is "one handle, one stream at a time" (include/ndcn_b200.h).  Solves from several Python threads
+# (or streams) serialise here instead of sharing state buffers; ranks-as-threads tests hold their own workspaces
+# (``peers=``) and are exempt.
+_SOLVE_LOCK = threading.RLock()
 
 
-def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """One reusable byte buffer per device, grown on demand (training loops call odeint
-    thousands of times with the same shapes)."""
-    key = (str(device), 0)
+def _workspace(device: torch.device, nbytes: int, stream: int = 0) -> torch.Tensor:
+    """One reusable byte buffer per (device, stream), grown on demand (training loops call odeint
+    thousands of times with the same shapes): solves enqueued on different streams never share state buffers."""
+    key = (str(device), int(stream))
     buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
@@ -278,45 +285,47 @@ def odeint_fused(graph: CsrGraph, spec: RhsSpec, y0: torch.Tensor, t: torch.Tens
         assert exchange is not None
         opts.gather_mode, opts.z_block_cols = _ffi.GATHER_EXTERNAL, int(z_block_cols)
     stats = _ffi.SolveStats()
-    with torch.cuda.device(dev):
-        nbytes = int(lib.ndcn_solver_workspace_bytes(graph.n_rows, graph.n_cols, spec.H, method_id))
-        if peers is not None:
-            if exchange is not None or z_block_cols or spec.callback is not None:
-                raise ValueError("peers= excludes exchange hooks and callback right-hand sides")
-            if graph is not peers.graph or peers.H != spec.H or peers.workspace_bytes < nbytes:
-                raise ValueError("peers was built for another graph / width / method")
-            ws_ptr, ws_bytes = peers.workspace_ptr, peers.workspace_bytes
-        else:
-            ws = _workspace(dev, nbytes)
-            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
-        # solver handles own pinned/ctrl scratch (cudaMallocHost is slow): keep a few alive,
-        # keyed on everything the handle captured by pointer
-        key = (id(graph), spec.kind, spec.flags, spec.H, method_id, desc.W, desc.b, tuple(spec.p),
-               ws_ptr, spec.callback is not None)
-        entry = _SOLVERS.get(key)
-        if entry is None or spec.callback is not None:
-            handle = C.c_void_p()
-            _ffi.check(lib.ndcn_solver_create(graph.handle, C.byref(desc), method_id, ws_ptr, ws_bytes,
-                                              C.byref(handle)), "ndcn_solver_create")
+    # ranks that run as threads of one process (peers=) meet in device barriers: they must NOT serialise here
+    with (_SOLVE_LOCK if peers is None else contextlib.nullcontext()):
+        with torch.cuda.device(dev):
+            nbytes = int(lib.ndcn_solver_workspace_bytes(graph.n_rows, graph.n_cols, spec.H, method_id))
             if peers is not None:
-                peers.configure(handle)
-            if len(_SOLVERS) >= 16:
-                oldest = next(iter(_SOLVERS))  # FIFO: never the handle another in-flight rank just created
-                old, _g = _SOLVERS.pop(oldest)
-                lib.ndcn_solver_destroy(old)
-            if spec.callback is None:
-                _SOLVERS[key] = (handle, graph)
-        else:
-            handle = entry[0]
-        try:
-            t_ptr = C.cast(t64.data_ptr(), _ffi.c_double_p)
-            entry = lib.ndcn_odeint_f32 if small is None else (lib.ndcn_odeint_small_f32 if small else
-                                                               lib.ndcn_odeint_staged_f32)
-            rc = entry(handle, y0.data_ptr(), t_ptr, n_t, out.data_ptr(), C.byref(opts), C.byref(stats),
-                       current_stream_ptr(dev))
-        finally:
-            if spec.callback is not None:
-                lib.ndcn_solver_destroy(handle)
+                if exchange is not None or z_block_cols or spec.callback is not None:
+                    raise ValueError("peers= excludes exchange hooks and callback right-hand sides")
+                if graph is not peers.graph or peers.H != spec.H or peers.workspace_bytes < nbytes:
+                    raise ValueError("peers was built for another graph / width / method")
+                ws_ptr, ws_bytes = peers.workspace_ptr, peers.workspace_bytes
+            else:
+                ws = _workspace(dev, nbytes, current_stream_ptr(dev))
+                ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+            # solver handles own pinned/ctrl scratch (cudaMallocHost is slow): keep a few alive,
+            # keyed on everything the handle captured by pointer
+            key = (id(graph), spec.kind, spec.flags, spec.H, method_id, desc.W, desc.b, tuple(spec.p),
+                   ws_ptr, spec.callback is not None)
+            entry = _SOLVERS.get(key)
+            if entry is None or spec.callback is not None:
+                handle = C.c_void_p()
+                _ffi.check(lib.ndcn_solver_create(graph.handle, C.byref(desc), method_id, ws_ptr, ws_bytes,
+                                                  C.byref(handle)), "ndcn_solver_create")
+                if peers is not None:
+                    peers.configure(handle)
+                if len(_SOLVERS) >= 16:
+                    oldest = next(iter(_SOLVERS))  # FIFO: never the handle another in-flight rank just created
+                    old, _g = _SOLVERS.pop(oldest)
+                    lib.ndcn_solver_destroy(old)
+                if spec.callback is None:
+                    _SOLVERS[key] = (handle, graph)
+            else:
+                handle = entry[0]
+            try:
+                t_ptr = C.cast(t64.data_ptr(), _ffi.c_double_p)
+                entry = lib.ndcn_odeint_f32 if small is None else (lib.ndcn_odeint_small_f32 if small else
+                                                                   lib.ndcn_odeint_staged_f32)
+                rc = entry(handle, y0.data_ptr(), t_ptr, n_t, out.data_ptr(), C.byref(opts), C.byref(stats),
+                           current_stream_ptr(dev))
+            finally:
+                if spec.callback is not None:
+                    lib.ndcn_solver_destroy(handle)
     if peers is not None:
         peers.n_solves += 1
     last_solve_info = SolveInfo(stats.nfe, stats.n_accepted, stats.n_rejected, stats.n_launches, stats.first_step,
