@@ -81,6 +81,9 @@ def parse_args():
     ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4, 5],
                     help="BASELINE.json preset: 0 north star (1M power-law, dopri5; default), 3 power-law 100489 nodes "
                          "RK4 (3/8 rule), 4 ER 1M dopri5, 5 power-law 4M dopri5; explicit flags override the preset")
+    ap.add_argument("--dt", type=float, default=None,
+                    help="step size (default T/100 = 0.05; the ground-truth dynamics on a power-law graph need ~1e-4: "
+                         "hub degrees in the thousands bound the stable step of an explicit method)")
     ap.add_argument("--rhs", choices=["ndcn", "heat", "gene", "mutual"], default="ndcn",
                     help="right-hand side: the NDCN ODEFunc (default) or a ground-truth dynamics (use --hidden 1)")
     args = ap.parse_args()
@@ -91,6 +94,9 @@ def parse_args():
     for k, v in preset.items():
         if k not in given:
             setattr(args, k, v)
+    if args.dt is not None:
+        global DT
+        DT = float(args.dt)
     return args
 
 

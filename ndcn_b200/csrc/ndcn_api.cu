@@ -1789,11 +1789,11 @@ static int run_small(Driver& d, const float* y0, const double* t, int n_t, float
   int grid = 0, rc = 0;
   sv->launches += 1;
   d.t_begin(NDCN_K_STAGE);
-  // one CTA, element-parallel, z in shared memory: the 400-node grid at H = 20, every small [N,d] dynamics state
+  // one CTA, element-parallel, block barriers: the small [N,d] ground-truth states (csrc/small_solver.cuh::tiny_stage)
   static const bool tiny_on = [] { const char* v = std::getenv("NDCN_TINY"); return !v || std::atoi(v) != 0; }();
-  const bool tiny = tiny_on && sv->numel <= kTinyMaxNumel && (sv->rhs.kind != NDCN_RHS_NDCN || sv->H <= 32);
+  const bool tiny = tiny_on && sv->numel <= kTinyMaxNumel && sv->rhs.kind != NDCN_RHS_NDCN;
   if (tiny) {
-    const size_t smem = sv->rhs.kind == NDCN_RHS_NDCN ? sizeof(float) * (size_t)sv->numel : 16;
+    const size_t smem = 16;
     SmallArgs copy = a;
     grid = 1;
     k_solve_small<0, 0, false, true><<<1, kTinyThreads, smem, st>>>(copy);

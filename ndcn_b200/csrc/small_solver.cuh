@@ -228,69 +228,39 @@ __device__ __noinline__ void small_stage(const SmallArgs& a, PtrPair src, const 
   epi_finish_block(e, err_acc);
 }
 
-// TINY: the whole problem on ONE CTA (<= 8192 state elements: the 400-node grid of the dynamics scripts at H=20, every
-// [N,1] ground-truth state).  Element-parallel instead of row-per-warp: thread e owns element (r, c) = (e / H, e % H) --
-// a few hundred rows cannot feed 16 warps row by row, but 8000 elements feed 512 threads -- with z = Phi x parked in
-// shared memory between the gather and the Linear.  Block barriers replace the grid barriers; everything the CTA
-// touches stays in its SM's L1.  Same accumulation orders as the row kernels (CSR order; k = 0..H-1): same bits.
-__device__ __noinline__ void tiny_stage(const SmallArgs& a, PtrPair src, const EpiArgs& e, float* zs, const float* wt_s) {
+// TINY: a whole [N,d] ground-truth solve on ONE CTA (<= 8192 state elements: the [400,1] states of the dynamics
+// scripts, heat_dynamics.py:207-209).  Element-parallel -- thread e owns element (r, c) = (e / d, e % d) and walks its
+// row's entries in CSR order -- with block barriers in place of the grid barriers: these solves take ~60-140 dopri5
+// steps of 7-9 phases whose work is a few hundred rows, so the barrier is the cost (measured: 1.71 ms against 2.84 ms
+// for the cooperative variant and 2.61 ms for 565 launches, 374 RHS evaluations of the heat ground truth).
+// (The NDCN right-hand side at H = 20 was tried the same way and lost -- 3.9 ms against 0.85 ms for 99 Euler steps:
+// one SM's 512 threads serialise 8000 x 28 multiply-adds per stage behind L2-latency loads of a state the CTA has
+// just written, where 50 cooperative CTAs spread them -- so NDCN stays on the cooperative variant.)
+__device__ __noinline__ void tiny_stage(const SmallArgs& a, PtrPair src, const EpiArgs& e) {
   EpiCtx c;
   if (!epi_resolve(e, c)) return;
   const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
   const float* __restrict__ x = sel(src, par);
   double err_acc = 0.0;
-  const int H = a.H;
+  const int d = a.H;
   const int numel = (int)a.numel;
-  if (a.kind == NDCN_RHS_NDCN) {
-    const bool no_graph = a.flags & NDCN_F_NO_GRAPH, no_control = a.flags & NDCN_F_NO_CONTROL;
-    const bool relu = !(a.flags & NDCN_F_NO_RELU);
-    for (int el = threadIdx.x; el < numel; el += blockDim.x) {
-      const int r = el / H, cc = el - r * H;
-      float s = 0.f;
-      if (no_graph) {
-        s = x[el];
-      } else {
-        const int start = a.g.rowptr[r], end = a.g.rowptr[r + 1];
-        for (int j = start; j < end; ++j) s = fmaf(__ldg(a.g.val + j), x[__ldg(a.g.col + j) * H + cc], s);
-      }
-      zs[el] = s;
+  for (int el = threadIdx.x; el < numel; el += blockDim.x) {
+    const int r = el / d, cc = el - r * d;
+    const float xi = x[el];
+    const int start = a.g.rowptr[r], end = a.g.rowptr[r + 1];
+    float s = 0.f;
+    for (int j = start; j < end; ++j) {
+      const float xj = x[__ldg(a.g.col + j) * d + cc];
+      const float av = __ldg(a.g.val + j);
+      if (a.kind == NDCN_RHS_HEAT) s = fadd(s, dyn_neighbour<NDCN_RHS_HEAT>(a.p, av, xi, xj, d == 1));
+      else if (a.kind == NDCN_RHS_GENE) s = fadd(s, dyn_neighbour<NDCN_RHS_GENE>(a.p, av, xi, xj, d == 1));
+      else s = fadd(s, dyn_neighbour<NDCN_RHS_MUTUAL>(a.p, av, xi, xj, d == 1));
     }
-    __syncthreads();
-    for (int el = threadIdx.x; el < numel; el += blockDim.x) {
-      const int r = el / H, cc = el - r * H;
-      float kv[1];
-      if (no_control) {
-        kv[0] = zs[el];
-      } else {
-        float t = 0.f;
-        const float* zr = zs + r * H;
-#pragma unroll 4
-        for (int k = 0; k < H; ++k) t = fmaf(zr[k], wt_s[k * 33 + cc], t);
-        kv[0] = t + __ldg(a.bias + cc);
-      }
-      if (relu) kv[0] = fmaxf(kv[0], 0.f);
-      epi_apply<1>(c, el, kv, err_acc);
-    }
-  } else {
-    const int d = H;
-    for (int el = threadIdx.x; el < numel; el += blockDim.x) {
-      const int r = el / d, cc = el - r * d;
-      const float xi = x[el];
-      const int start = a.g.rowptr[r], end = a.g.rowptr[r + 1];
-      float s = 0.f;
-      for (int j = start; j < end; ++j) {
-        const float xj = x[__ldg(a.g.col + j) * d + cc];
-        const float av = __ldg(a.g.val + j);
-        if (a.kind == NDCN_RHS_HEAT) s = fadd(s, dyn_neighbour<NDCN_RHS_HEAT>(a.p, av, xi, xj, d == 1));
-        else if (a.kind == NDCN_RHS_GENE) s = fadd(s, dyn_neighbour<NDCN_RHS_GENE>(a.p, av, xi, xj, d == 1));
-        else s = fadd(s, dyn_neighbour<NDCN_RHS_MUTUAL>(a.p, av, xi, xj, d == 1));
-      }
-      float kv[1];
-      if (a.kind == NDCN_RHS_HEAT) kv[0] = dyn_local<NDCN_RHS_HEAT>(a.p, xi, s);
-      else if (a.kind == NDCN_RHS_GENE) kv[0] = dyn_local<NDCN_RHS_GENE>(a.p, xi, s);
-      else kv[0] = dyn_local<NDCN_RHS_MUTUAL>(a.p, xi, s);
-      epi_apply<1>(c, el, kv, err_acc);
-    }
+    float kv[1];
+    if (a.kind == NDCN_RHS_HEAT) kv[0] = dyn_local<NDCN_RHS_HEAT>(a.p, xi, s);
+    else if (a.kind == NDCN_RHS_GENE) kv[0] = dyn_local<NDCN_RHS_GENE>(a.p, xi, s);
+    else kv[0] = dyn_local<NDCN_RHS_MUTUAL>(a.p, xi, s);
+    epi_apply<1>(c, el, kv, err_acc);
   }
   epi_finish_block(e, err_acc);
 }
@@ -352,13 +322,12 @@ __device__ __forceinline__ double small_sum_partials(const double* partials, int
   } while (0)
 
 constexpr int kTinyThreads = 512;
-constexpr int kTinyMaxNumel = 8192;  // z = Phi x of the whole state in shared memory (32 KB)
+constexpr int kTinyMaxNumel = 8192;
 
 template <int VW, int NCH, bool CONTROL, bool TINY = false>
 __global__ void __launch_bounds__(TINY ? kTinyThreads : kStageThreads, (TINY || (VW > 0 && CONTROL)) ? 1 : 2)
 k_solve_small(const __grid_constant__ SmallArgs a) {
-  // VW == 0: [warps][max(H, 32)] scratch rows of the row-per-warp right-hand side; tiled GEMM: GemmSmem<VW, NCH>;
-  // TINY: z = Phi x of the whole state, [numel]
+  // VW == 0: [warps][max(H, 32)] scratch rows of the row-per-warp right-hand side; tiled GEMM: GemmSmem<VW, NCH>
   extern __shared__ __align__(128) float zs[];
   __shared__ double s_tmp[TINY ? kTinyThreads : kStageThreads];
   __shared__ float s_xs[kEmitMaxPerLaunch * 4];
@@ -377,7 +346,7 @@ k_solve_small(const __grid_constant__ SmallArgs a) {
   __syncthreads();
 #define NDCN_STAGE(src)                                                             \
   do {                                                                              \
-    if constexpr (TINY) tiny_stage(a, src, s_run, zs, s_wt);                        \
+    if constexpr (TINY) tiny_stage(a, src, s_run);                        \
     else small_stage<VW, NCH, CONTROL>(a, src, s_run, zs, s_wt, chunk_it);          \
   } while (0)
 #define NDCN_BAR()                                  \
