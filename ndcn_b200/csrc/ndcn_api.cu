@@ -40,6 +40,7 @@ struct ndcn_graph {
   int32_t* long_rows = nullptr;  // rows with more than kLongRow entries (device)
   int n_long = 0;
   int max_deg = 0;
+  std::vector<int32_t> long_host;  // the same list on the host, ascending (row-chunked gathers take sub-ranges)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -50,6 +51,7 @@ struct Config {
   int gather_cw = 0;                // 0 auto, -1 full-row gather, else chunk width in floats (16/32/64)
   int64_t umma_min_rows = 8192;     // auto: tcgen05 path from this many rows
   int gather_v = 1;                 // chunk-major gather flavour: 1 one row per lane group, 2 persistent + TMA-staged CSR
+  int64_t z_chunk_rows = 0;         // > 0: gather and tcgen05 stage kernel alternate over row chunks of this size (Z in L2)
   int small_solver = 1;             // 1: solves that fit the persistent whole-solve kernel use it (ndcn_odeint_f32 auto)
   int64_t small_max_rows = 16384;   // ... up to this many rows
   int64_t small_max_numel = 1 << 21;  // ... and this many state elements (8 MB per buffer: everything stays in L2)
@@ -62,6 +64,7 @@ static Config& cfg() {
     if (const char* v = std::getenv("NDCN_UMMA_MIN_ROWS")) k.umma_min_rows = std::atoll(v);
     if (const char* v = std::getenv("NDCN_GATHER_V")) k.gather_v = std::atoi(v);
     if (const char* v = std::getenv("NDCN_SMALL_SOLVER")) k.small_solver = std::atoi(v) != 0;
+    if (const char* v = std::getenv("NDCN_Z_CHUNK_ROWS")) k.z_chunk_rows = std::atoll(v) / kUmmaM * kUmmaM;
     return k;
   }();
   return c;
@@ -281,7 +284,7 @@ static int launch_dyn(const DynArgs& a, EpiArgs& e, double avg_deg, int* grid_ou
     else if (avg_deg > 12) lpr = 16;
     else if (avg_deg > 6) lpr = 8;
     const int64_t rows_per_block = (int64_t)kStageThreads / lpr;
-    const int grid = (int)((n + rows_per_block - 1) / rows_per_block);
+    const int grid = (int)((n + rows_per_block - 1) / rows_per_block) + a.n_long;
     *grid_out = grid;
     switch (lpr) {
       case 4: k_stage_dyn1<KIND, 4><<<grid, kStageThreads, 0, st>>>(a, e); break;
@@ -298,7 +301,7 @@ static int launch_dyn(const DynArgs& a, EpiArgs& e, double avg_deg, int* grid_ou
 }
 
 struct StageTimer {  // optional per-launch timing hook (Driver implements it)
-  virtual void begin(int cls) = 0;
+  virtual void begin(int cls, bool count = true) = 0;  // count: this launch opens a new RHS evaluation (vs another chunk of it)
   virtual void end() = 0;
 };
 
@@ -418,7 +421,7 @@ static int launch_umma_inst(const UmmaArgs& u, EpiArgs& e, int grid, cudaStream_
 // one instantiation per Runge-Kutta stage shape (epilogue mode x number of earlier stages read)
 template <int H>
 static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_out, cudaStream_t st) {
-  const int64_t n_tiles = (u.n_rows + kUmmaM - 1) / kUmmaM;
+  const int64_t n_tiles = u.tile_end > 0 ? u.tile_end - u.tile_begin : (u.n_rows + kUmmaM - 1) / kUmmaM;
   const int grid = (int)std::min<int64_t>(n_tiles, sm_count);
   *grid_out = grid;
   if (grid == 0) return 0;
@@ -513,6 +516,8 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
   };
   if (r.kind == NDCN_RHS_NDCN) {
     NdcnArgs a;
+    a.row_begin = a.row_end = 0;
+    a.keep_l2 = 0;
     a.g = b.g->v;
     a.x = src;
     a.Wt = b.Wt;
@@ -531,21 +536,9 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
       UmmaArgs u;
       u.z = src;
       u.z_block_log2 = 0;
+      u.tile_begin = u.tile_end = 0;
+      u.partials_off = 0;
       for (int w = external_z ? b.z_block_cols : r.H; w > 1; w >>= 1) u.z_block_log2 += 1;
-      if (external_z) {
-        u.z = pp(b.Z);  // the exchange hook has filled it (Driver::stage)
-      } else if (!(r.flags & NDCN_F_NO_GRAPH)) {
-        NdcnArgs ga = a;
-        ga.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
-        EpiArgs se = store_only(b.Z);
-        se.ctrl = e.ctrl;  // same buffer parity / done flag as the stage that consumes Z
-        int g2 = 0;
-        tick(NDCN_K_GATHER);
-        rc = launch_gather(b, ga, r.H, se, &g2, st);
-        tock();
-        if (rc != 0) return rc;
-        u.z = pp(b.Z);
-      }
       u.wimg = b.Wimg;
       u.bias = r.b;
       u.n_rows = a.g.n_rows;
@@ -557,9 +550,68 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
         }();
         u.deep_batch = (dbg >> 8) & 1u;
       }
-      tick(NDCN_K_STAGE);
-      rc = r.H == 256 ? launch_umma<256>(u, e, b.sm_count, &grid, st) : launch_umma<128>(u, e, b.sm_count, &grid, st);
-      tock();
+      const int64_t chunk = cfg().z_chunk_rows;
+      if (!external_z && !(r.flags & NDCN_F_NO_GRAPH) && chunk > 0 && a.g.n_rows > 2 * chunk &&
+          pick_gather_cw(a.g.n_cols, r.H) == 0 && (r.H == 256 || r.H == 128)) {
+        // Z L2-resident: gather and stage kernel alternate over row chunks; the chunk's z lives in one of two
+        // chunk-sized halves of Z (plain stores, read back out of L2 by the A producers' streaming loads)
+        const std::vector<int32_t>& lh = b.g->long_host;
+        size_t lo = 0;
+        int ci = 0, p_off = 0;
+        for (int64_t r0 = 0; r0 < a.g.n_rows; r0 += chunk, ++ci) {
+          const int64_t r1 = std::min<int64_t>(a.g.n_rows, r0 + chunk);
+          float* buf = b.Z + (size_t)(ci & 1) * chunk * r.H;
+          float* zbase = buf - (size_t)r0 * r.H;  // row index stays global
+          size_t hi = lo;
+          while (hi < lh.size() && lh[hi] < r1) ++hi;
+          NdcnArgs ga = a;
+          ga.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+          ga.row_begin = r0;
+          ga.row_end = r1;
+          ga.keep_l2 = 1;
+          ga.long_rows = b.g->long_rows + lo;
+          ga.n_long = (int)(hi - lo);
+          lo = hi;
+          EpiArgs se = store_only(zbase);
+          se.ctrl = e.ctrl;
+          const int ggrid = (int)((r1 - r0 + kWarpsPerCta - 1) / kWarpsPerCta) + ga.n_long;
+          if (b.timer) b.timer->begin(NDCN_K_GATHER, ci == 0);
+          if (b.launches) *b.launches += 1;
+          if (r.H == 256) k_stage_ndcn_row<4, 2, 4, 4, true><<<ggrid, kStageThreads, 0, st>>>(ga, se);
+          else k_stage_ndcn_row<4, 1, 8, 5, true><<<ggrid, kStageThreads, 0, st>>>(ga, se);
+          tock();
+          u.z = pp(zbase);
+          u.tile_begin = r0 / kUmmaM;
+          u.tile_end = (r1 + kUmmaM - 1) / kUmmaM;
+          u.partials_off = p_off;
+          if (b.timer) b.timer->begin(NDCN_K_STAGE, ci == 0);
+          if (b.launches) *b.launches += 1;
+          int cgrid = 0;
+          rc = r.H == 256 ? launch_umma<256>(u, e, b.sm_count, &cgrid, st) : launch_umma<128>(u, e, b.sm_count, &cgrid, st);
+          tock();
+          if (rc != 0) return rc;
+          p_off += cgrid;
+        }
+        grid = p_off;
+      } else {
+        if (external_z) {
+          u.z = pp(b.Z);  // the exchange hook has filled it (Driver::stage)
+        } else if (!(r.flags & NDCN_F_NO_GRAPH)) {
+          NdcnArgs ga = a;
+          ga.flags = NDCN_F_NO_CONTROL | NDCN_F_NO_RELU;
+          EpiArgs se = store_only(b.Z);
+          se.ctrl = e.ctrl;  // same buffer parity / done flag as the stage that consumes Z
+          int g2 = 0;
+          tick(NDCN_K_GATHER);
+          rc = launch_gather(b, ga, r.H, se, &g2, st);
+          tock();
+          if (rc != 0) return rc;
+          u.z = pp(b.Z);
+        }
+        tick(NDCN_K_STAGE);
+        rc = r.H == 256 ? launch_umma<256>(u, e, b.sm_count, &grid, st) : launch_umma<128>(u, e, b.sm_count, &grid, st);
+        tock();
+      }
     } else if (!need_w && src_aligned && pick_gather_cw(a.g.n_cols, r.H) > 0) {
       tick(NDCN_K_STAGE);
       rc = launch_gather(b, a, r.H, e, &grid, st);
@@ -587,6 +639,8 @@ static int launch_stage(const RhsBinding& b, PtrPair src, EpiArgs e, int* n_part
     a.kind = r.kind;
     a.d = r.H;
     for (int i = 0; i < 8; ++i) a.p[i] = r.p[i];
+    a.long_rows = b.g->long_rows;
+    a.n_long = r.H == 1 ? b.g->n_long : 0;
     const double avg = a.g.n_rows > 0 ? (double)a.g.nnz / (double)a.g.n_rows : 0.0;
     tick(NDCN_K_STAGE);
     if (r.kind == NDCN_RHS_HEAT) rc = launch_dyn<NDCN_RHS_HEAT>(a, e, avg, &grid, st);
@@ -607,8 +661,9 @@ static int max_partials_for(const ndcn_graph* g, int H) {
   // warp-per-row kernels, and the chunk-major gather (H/cw chunks x (row blocks + long rows))
   const int64_t n_rows = g->v.n_rows;
   int64_t by_rows = (n_rows + (kStageThreads / 32) - 1) / (kStageThreads / 32) + g->n_long;
-  int64_t by_lpr4 = (n_rows + 63) / 64;
-  int64_t best = std::max<int64_t>(std::max(by_rows, by_lpr4), (int64_t)sm_count_now() * 16);  // grid_for_elems' cap
+  int64_t by_lpr4 = (n_rows + 63) / 64 + g->n_long;
+  // grid_for_elems' cap; row-chunked tcgen05 launches write one partial per CTA and chunk
+  int64_t best = std::max<int64_t>(std::max(by_rows, by_lpr4), (int64_t)sm_count_now() * 64);
   if (H % 16 == 0) {
     const int cws[3] = {16, 32, 64};
     for (int cw : cws)
@@ -652,6 +707,7 @@ extern "C" int ndcn_graph_create(int64_t n_rows, int64_t n_cols, int64_t nnz, co
       if (deg > kLongRow) longs.push_back((int32_t)r);
     }
     g->n_long = (int)longs.size();
+    g->long_host = longs;
     if (g->n_long > 0) {
       ce = cudaMalloc((void**)&g->long_rows, sizeof(int32_t) * longs.size());
       if (ce == cudaSuccess)
@@ -1146,15 +1202,15 @@ struct Driver : StageTimer {
   }
 
   // ---- optional per-class kernel timing (NDCN_O_TIME_KERNELS): CUDA events on the launch stream
-  struct Ev { cudaEvent_t a, b; int cls; int64_t attempt; };
+  struct Ev { cudaEvent_t a, b; int cls; int64_t attempt; bool count; };
   bool timing = false;
   int64_t cur_attempt = -1;  // dopri5 attempt index the next launches belong to (-1: prologue)
   std::vector<Ev> evs;
-  void begin(int cls) override { t_begin(cls); }
+  void begin(int cls, bool count) override { t_begin(cls, count); }
   void end() override { t_end(); }
-  void t_begin(int cls) {
+  void t_begin(int cls, bool count = true) {
     if (!timing) return;
-    Ev e{nullptr, nullptr, cls, cur_attempt};
+    Ev e{nullptr, nullptr, cls, cur_attempt, count};
     cudaEventCreate(&e.a);
     cudaEventCreate(&e.b);
     cudaEventRecord(e.a, st);
@@ -1169,7 +1225,7 @@ struct Driver : StageTimer {
       float ms = 0.f;
       if (stats && (e.attempt < 0 || e.attempt < n_real) && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
         stats->class_ms[e.cls] += (double)ms;
-        stats->class_launches[e.cls] += 1;
+        if (e.count) stats->class_launches[e.cls] += 1;
       }
       cudaEventDestroy(e.a);
       cudaEventDestroy(e.b);

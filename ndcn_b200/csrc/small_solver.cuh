@@ -175,6 +175,7 @@ __device__ __noinline__ void small_stage(const SmallArgs& a, PtrPair src, const 
   if (a.kind == NDCN_RHS_NDCN) {
     NdcnArgs na;
     na.g = a.g; na.x = src; na.Wt = a.Wt; na.bias = a.bias; na.flags = a.flags; na.long_rows = nullptr; na.n_long = 0;
+    na.row_begin = 0; na.row_end = 0; na.keep_l2 = 0;
     if constexpr (VW > 0 && CONTROL) {
       const int64_t n_tiles = ((int64_t)a.n_rows + kTileRows - 1) / kTileRows;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -206,7 +207,7 @@ __device__ __noinline__ void small_stage(const SmallArgs& a, PtrPair src, const 
     }
   } else {
     DynArgs da;
-    da.g = a.g; da.x = src; da.kind = a.kind; da.d = a.H;
+    da.g = a.g; da.x = src; da.kind = a.kind; da.d = a.H; da.long_rows = nullptr; da.n_long = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) da.p[i] = a.p[i];
     if (a.H == 1) {

@@ -96,6 +96,10 @@ struct NdcnArgs {
   uint32_t flags;     // NDCN_F_*
   const int32_t* long_rows;  // rows with more than kLongRow entries (may be null)
   int n_long;
+  // row-chunked store-only gather: rows [row_begin, row_end) only (row_end == 0: all rows); long_rows / n_long then
+  // name the chunk's long rows; keep_l2: plain stores (the consumer reads the chunk out of L2), not streaming ones
+  int64_t row_begin, row_end;
+  int keep_l2;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -127,9 +131,14 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs
   const int n_long = graph ? a.n_long : 0;
   double err_acc = 0.0;
   auto finish = [&](int64_t off, float (&v)[VW]) {
-    if constexpr (STORE_ONLY) stv_stream<VW>(zout + off, v);
-    else epi_apply<VW>(c, off, v, err_acc);
+    if constexpr (STORE_ONLY) {
+      if (a.keep_l2) stv<VW>(zout + off, v);
+      else stv_stream<VW>(zout + off, v);
+    } else {
+      epi_apply<VW>(c, off, v, err_acc);
+    }
   };
+  const int64_t row_end = a.row_end > 0 ? a.row_end : a.g.n_rows;
   if ((int)blockIdx.x < n_long) {
     const int64_t row = __ldg(a.long_rows + blockIdx.x);
     const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
@@ -158,8 +167,8 @@ __global__ void __launch_bounds__(kStageThreads, MINB) k_stage_ndcn_row(NdcnArgs
       }
     }
   } else {
-    const int64_t row = (int64_t)(blockIdx.x - n_long) * kWarpsPerCta + warp;
-    if (row < a.g.n_rows) {
+    const int64_t row = a.row_begin + (int64_t)(blockIdx.x - n_long) * kWarpsPerCta + warp;
+    if (row < row_end) {
       float acc[NCH][VW];
       bool mine = true;
       if (!graph) {
@@ -422,6 +431,11 @@ struct DynArgs {
   int kind;   // NDCN_RHS_HEAT / GENE / MUTUAL
   int d;      // state width
   float p[8];
+  // [N,1] kernel: rows above kLongRow entries get a CTA each (the first n_long CTAs of the grid): a power-law hub
+  // (thousands of entries) would otherwise be walked by LPR lanes, one dependent load chain after the other --
+  // measured 0.3 ms per evaluation at 1M nodes for 0.05 ms of real work
+  const int32_t* long_rows;
+  int n_long;
 };
 
 // torch.pow semantics for the exponents the scripts use (1, 2) are exact products
@@ -473,9 +487,15 @@ __device__ __forceinline__ void dyn1_warp_rows(const DynArgs& a, const float* __
   const int64_t row = row_base + lane / LPR;
   const int sub = lane % LPR;
   float s = 0.f, xi = 0.f;
+  bool mine = true;  // false: a long row, produced by its own CTA
   if (row < a.g.n_rows) {
     xi = x[row];
-    const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
+    const int start = __ldg(a.g.rowptr + row);
+    int end = __ldg(a.g.rowptr + row + 1);
+    if (a.n_long > 0 && end - start > kLongRow) {
+      mine = false;
+      end = start;
+    }
     for (int j = start + sub; j < end; j += LPR) {
       const float xj = x[__ldg(a.g.col + j)];
       s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, xj, true));
@@ -486,8 +506,9 @@ __device__ __forceinline__ void dyn1_warp_rows(const DynArgs& a, const float* __
   float kval = dyn_local<KIND>(a.p, xi, s);
   // lane i < RPWARP takes the result of row row_base + i (held by lane i*LPR)
   kval = __shfl_sync(0xffffffffu, kval, (lane * LPR) & 31);
+  mine = __shfl_sync(0xffffffffu, mine ? 1 : 0, (lane * LPR) & 31) != 0;
   const int64_t my_row = row_base + lane;
-  if (lane < RPWARP && my_row < a.g.n_rows) {
+  if (lane < RPWARP && my_row < a.g.n_rows && mine) {
     float kv[1] = {kval};
     epi_apply<1>(c, my_row, kv, err_acc);
   }
@@ -495,12 +516,34 @@ __device__ __forceinline__ void dyn1_warp_rows(const DynArgs& a, const float* __
 
 template <int KIND, int LPR>
 __global__ void __launch_bounds__(kStageThreads) k_stage_dyn1(DynArgs a, EpiArgs e) {
+  __shared__ float s_sum[kStageThreads / 32];
   EpiCtx c;
   if (!epi_resolve(e, c)) return;
   const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
   const float* __restrict__ x = sel(a.x, par);
   double err_acc = 0.0;
-  dyn1_warp_rows<KIND, LPR>(a, x, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31, c, err_acc);
+  if ((int)blockIdx.x < a.n_long) {
+    // one long row: the CTA's threads stride over its entries; lanes, then warps, are added in a fixed order
+    const int64_t row = __ldg(a.long_rows + blockIdx.x);
+    const float xi = x[row];
+    const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
+    float s = 0.f;
+    for (int j = start + (int)threadIdx.x; j < end; j += kStageThreads)
+      s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, x[__ldg(a.g.col + j)], true));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fadd(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kStageThreads / 32; ++w) tot = fadd(tot, s_sum[w]);
+      float kv[1] = {dyn_local<KIND>(a.p, xi, tot)};
+      epi_apply<1>(c, row, kv, err_acc);
+    }
+  } else {
+    dyn1_warp_rows<KIND, LPR>(a, x, ((int64_t)(blockIdx.x - a.n_long) * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31,
+                              c, err_acc);
+  }
   epi_finish_block(e, err_acc);
 }
 

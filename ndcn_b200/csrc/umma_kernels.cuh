@@ -173,6 +173,10 @@ struct UmmaArgs {
   // delivers one [n_rows, H/P] block per peer and nobody has to interleave them)
   int z_block_log2;
   uint32_t deep_batch; // experiment switch (NDCN_UMMA_DBG=256): the other epilogue batch depth
+  // row-chunked launches (Z kept L2-resident between its gather and this kernel): tiles [tile_begin, tile_end) only
+  // (0, 0 = all tiles); the error partial of CTA b goes to partials[partials_off + b]
+  int64_t tile_begin, tile_end;
+  int partials_off;
 };
 
 // MODE / NPREV: the epilogue mode and the number of earlier stages it reads are compile-time
@@ -202,7 +206,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
   uint64_t* tmem_empty = bars + 6;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int64_t n_tiles = (a.n_rows + kUmmaM - 1) / kUmmaM;
+  const int64_t all_tiles = (a.n_rows + kUmmaM - 1) / kUmmaM;
+  const int64_t n_tiles = a.tile_end > 0 ? a.tile_end - a.tile_begin : all_tiles;
+  const int64_t tile0 = a.tile_begin + (int64_t)blockIdx.x;  // this CTA's first tile
   const int64_t my_tiles = (n_tiles - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;  // blockIdx.x < n_tiles
 
   if (threadIdx.x == 0) {
@@ -246,12 +252,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     auto prefetch_chunk = [&](int64_t g) {
       const int64_t ti = g / kChunks;
       if (ti >= my_tiles) return;
-      const int64_t row = ((int64_t)blockIdx.x + ti * gridDim.x) * kUmmaM + q * 32 + lane;
+      const int64_t row = (tile0 + ti * gridDim.x) * kUmmaM + q * 32 + lane;
       if (row < a.n_rows) epi_prefetch_l2_last(c, row * H + half * (H / 2) + (int)(g % kChunks) * 32);
     };
     for (int g = 0; g < kAhead; ++g) prefetch_chunk(g);
     for (int64_t i = 0; i < my_tiles; ++i) {
-      const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+      const int64_t tile = tile0 + i * gridDim.x;
       const int acc = (int)(i & 1);
       const int64_t row_base = tile * kUmmaM + q * 32;
       mbar_wait(&tmem_full[acc], (uint32_t)((i >> 1) & 1));
@@ -384,7 +390,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
       return z + (int64_t)(col0 >> bl) * blk_stride + (row << bl) + (col0 & ((1 << bl) - 1));
     };
     auto load_atom = [&](int64_t it, float4(&dst)[8]) {
-      const int64_t tile = (int64_t)blockIdx.x + (it / Cf::kAtoms) * gridDim.x;
+      const int64_t tile = tile0 + (it / Cf::kAtoms) * gridDim.x;
       const int atom = (int)(it % Cf::kAtoms);
       const int64_t row0 = tile * kUmmaM + pw * 32 + rsub;
 #pragma unroll
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     // lane r of producer warp pw prefetches (L2) the 128-byte atom row r of its 32 rows
     auto prefetch_atom = [&](int64_t it) {
       if (it >= total) return;
-      const int64_t tile = (int64_t)blockIdx.x + (it / Cf::kAtoms) * gridDim.x;
+      const int64_t tile = tile0 + (it / Cf::kAtoms) * gridDim.x;
       const int64_t row = tile * kUmmaM + pw * 32 + lane;
       if (row < a.n_rows) prefetch_l2(z_atom(row, (int)(it % Cf::kAtoms)));
     };
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_stage_gemm_umma(UmmaArgs a,
     if (threadIdx.x == 0) {
       double v = 0.0;
       for (int w = 0; w < kUmmaThreads / 32; ++w) v += red[w];
-      e.partials[blockIdx.x] = v;
+      e.partials[a.partials_off + blockIdx.x] = v;
     }
   }
   if (warp == kUmmaMmaWarp) {
