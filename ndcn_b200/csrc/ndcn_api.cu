@@ -278,7 +278,12 @@ static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaSt
 template <int KIND>
 static int launch_dyn(const DynArgs& a, EpiArgs& e, double avg_deg, int* grid_out, cudaStream_t st) {
   const int64_t n = a.g.n_rows;
-  if (a.d == 1) {
+  if (a.d == 1 && n >= 32768) {
+    // at scale: CSR-stream kernel (slice staged in shared memory, entry-parallel terms, CSR-order row sums)
+    const int grid = (int)((n + kDynRows - 1) / kDynRows) + a.n_long;
+    *grid_out = grid;
+    k_stage_dyn1_stream<KIND><<<grid, kStageThreads, 0, st>>>(a, e);
+  } else if (a.d == 1) {
     int lpr = 4;
     if (avg_deg > 24) lpr = 32;
     else if (avg_deg > 12) lpr = 16;

@@ -81,6 +81,14 @@ __device__ __forceinline__ void small_blank(EpiArgs& e) {
   e.e_out = nullptr; e.err_prefix = 0;
 }
 
+// descriptor copy between two shared-memory EpiArgs by the whole CTA (word-wise)
+__device__ __forceinline__ void small_copy_desc(EpiArgs* dst, const EpiArgs* src) {
+  static_assert(sizeof(EpiArgs) % 4 == 0, "EpiArgs is copied word-wise");
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(EpiArgs) / 4); i += blockDim.x) d[i] = s[i];
+}
+
 // the zero-coefficient streams of a stage are not read (see drop_zero_terms in ndcn_api.cu: same rule, same bits)
 __device__ __forceinline__ void small_drop_zero_terms(EpiArgs& e) {
   if (e.mode != EPI_LINCOMB && e.mode != EPI_ERR && e.mode != EPI_LINCOMB_E) return;
@@ -311,15 +319,16 @@ __device__ __forceinline__ double small_sum_partials(const double* partials, int
 // thread 0 edits the stage descriptor in shared memory; PUBLISH makes it visible to the CTA (the grid barrier
 // that follows every stage keeps the next edit from overtaking a reader)
 #define NDCN_T0 if (threadIdx.x == 0)
-#define NDCN_PUBLISH()                              \
-  do {                                              \
-    __syncthreads();                                \
-    NDCN_T0 {                                       \
-      s_run = s_e;                                  \
-      s_run.partials = a.partials;                  \
-      small_drop_zero_terms(s_run);                 \
-    }                                               \
-    __syncthreads();                                \
+#define NDCN_PUBLISH()                                                                        \
+  do {                                                                                        \
+    __syncthreads();                                                                          \
+    small_copy_desc(&s_run, &s_e); /* all threads, one word each: not 110 serial copies */   \
+    __syncthreads();                                                                          \
+    NDCN_T0 {                                                                                 \
+      s_run.partials = a.partials;                                                            \
+      small_drop_zero_terms(s_run);                                                           \
+    }                                                                                         \
+    __syncthreads();                                                                          \
   } while (0)
 
 constexpr int kTinyThreads = 512;
@@ -703,7 +712,7 @@ __global__ void __launch_bounds__(kStageThreads, 2) k_adjoint_small(const __grid
 #define ADJ_STAGE(src)                                                                    \
   do {                                                                                    \
     __syncthreads();                                                                      \
-    ADJ_T0 { s_run = s_e; s_run.partials = nullptr; }                                     \
+    small_copy_desc(&s_run, &s_e);                                                        \
     __syncthreads();                                                                      \
     small_stage<0, 0, false>(fw, src, s_run, zs, s_wt, chunk_it);                         \
     grid.sync();                                                                          \

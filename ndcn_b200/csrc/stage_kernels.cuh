@@ -547,6 +547,108 @@ __global__ void __launch_bounds__(kStageThreads) k_stage_dyn1(DynArgs a, EpiArgs
   epi_finish_block(e, err_acc);
 }
 
+// [N,1] state at scale ("CSR-stream"): a CTA owns 256 consecutive rows.  Their (col, val) slice is contiguous: it is
+// staged in shared memory with coalesced loads, then the CTA's threads evaluate the per-ENTRY terms
+// a_ij g(x_i, x_j) entry-parallel -- thread t takes entries t, t + 256, ... whatever row they belong to, with 4
+// independent x[col] loads in flight -- and park them in shared memory; finally thread r adds the terms of row r in
+// CSR order (the order torch.sparse.mm's CPU kernel uses) and runs the stage epilogue on consecutive rows (coalesced).
+// The lane-group kernel above walks every row behind its own chain of dependent loads (rowptr -> col -> x): at 1M rows
+// of ~11 entries that chain, not bandwidth, set its 0.25 ms per evaluation.  Slices larger than the staging buffer are
+// processed in rounds; rows above kLongRow entries keep their own CTAs.
+constexpr int kDynRows = 256;
+constexpr int kDynCap = 4096;
+
+template <int KIND>
+__global__ void __launch_bounds__(kStageThreads) k_stage_dyn1_stream(DynArgs a, EpiArgs e) {
+  __shared__ int s_rp[kDynRows + 1];
+  __shared__ float s_xi[kDynRows];
+  __shared__ int s_col[kDynCap];
+  __shared__ float s_val[kDynCap];  // values, then the per-entry terms
+  __shared__ float s_sum[kStageThreads / 32];
+  EpiCtx c;
+  if (!epi_resolve(e, c)) return;
+  const int par = e.ctrl ? ((volatile Ctrl*)e.ctrl)->parity : 0;
+  const float* __restrict__ x = sel(a.x, par);
+  double err_acc = 0.0;
+  if ((int)blockIdx.x < a.n_long) {
+    const int64_t row = __ldg(a.long_rows + blockIdx.x);
+    const float xi = x[row];
+    const int start = __ldg(a.g.rowptr + row), end = __ldg(a.g.rowptr + row + 1);
+    float s = 0.f;
+    for (int j = start + (int)threadIdx.x; j < end; j += kStageThreads)
+      s = fadd(s, dyn_neighbour<KIND>(a.p, __ldg(a.g.val + j), xi, x[__ldg(a.g.col + j)], true));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fadd(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kStageThreads / 32; ++w) tot = fadd(tot, s_sum[w]);
+      float kv[1] = {dyn_local<KIND>(a.p, xi, tot)};
+      epi_apply<1>(c, row, kv, err_acc);
+    }
+  } else {
+    const int64_t r0 = (int64_t)(blockIdx.x - a.n_long) * kDynRows;
+    const int nr = (int)min((int64_t)kDynRows, a.g.n_rows - r0);
+    const int t = threadIdx.x;
+    for (int i = t; i <= nr; i += kStageThreads) s_rp[i] = __ldg(a.g.rowptr + r0 + i);
+    if (t < nr) s_xi[t] = x[r0 + t];
+    __syncthreads();
+    const int e0 = s_rp[0], e1 = s_rp[nr];
+    int my_start = 0, my_end = 0;
+    bool mine = false;
+    if (t < nr) {
+      my_start = s_rp[t];
+      my_end = s_rp[t + 1];
+      mine = !(a.n_long > 0 && my_end - my_start > kLongRow);
+    }
+    float s = 0.f;
+    for (int base = e0; base < e1; base += kDynCap) {
+      const int cnt = min(kDynCap, e1 - base);
+      for (int i = t; i < cnt; i += kStageThreads) {
+        s_col[i] = __ldcs(a.g.col + base + i);
+        s_val[i] = __ldcs(a.g.val + base + i);
+      }
+      __syncthreads();
+      // entry-parallel terms, 4 independent x loads in flight per thread
+      for (int i0 = t; i0 < cnt; i0 += 4 * kStageThreads) {
+        float xj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kStageThreads;
+          xj[u] = i < cnt ? x[s_col[i]] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kStageThreads;
+          if (i < cnt) {
+            // row of entry (base + i): the last r with s_rp[r] <= base + i
+            const int ge = base + i;
+            int lo = 0, hi = nr;
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (s_rp[mid] <= ge) lo = mid;
+              else hi = mid;
+            }
+            s_val[i] = dyn_neighbour<KIND>(a.p, s_val[i], s_xi[lo], xj[u], true);
+          }
+        }
+      }
+      __syncthreads();
+      if (mine) {
+        const int lo = max(my_start, base) - base, hi = min(my_end, base + cnt) - base;
+        for (int i = lo; i < hi; ++i) s = fadd(s, s_val[i]);
+      }
+      __syncthreads();
+    }
+    if (mine) {
+      float kv[1] = {dyn_local<KIND>(a.p, s_xi[t], s)};
+      epi_apply<1>(c, r0 + t, kv, err_acc);
+    }
+  }
+  epi_finish_block(e, err_acc);
+}
+
 // [N,d] state, d > 1: one warp per row, lanes over the d columns.
 template <int KIND>
 __device__ __forceinline__ void dynv_row(const DynArgs& a, const float* __restrict__ x, int64_t row, int lane,
