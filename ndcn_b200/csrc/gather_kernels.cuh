@@ -378,10 +378,14 @@ constexpr int kSlabCap = 2048;
 // `rb_shift`: the grid walks the row blocks starting at this one (wrapping around).  Every rank of the feature-sharded
 // push gathers ALL rows and stores z to the rows' owners in the same order; a per-rank start (rank q at its own block)
 // keeps the ranks on different owners at any moment.  Measured: no gain (see the caller), default 0.
+// `spread` > 1: consecutive CTAs take row blocks of DIFFERENT owners (block index b -> owner b % spread, the owner's
+// (b / spread)-th block): the CTAs resident at any moment store to all owners at once, so that no GPU's NVLink ingress
+// is the target of every sender at the same time; n_rb is then spread * ceil(real blocks / spread) and the surplus
+// indices do nothing.
 __global__ void __launch_bounds__(kStageThreads, 6) k_gather_slab(GraphView g, const float* __restrict__ x,
                                                                   int64_t n_src, int n_rb, int n_long,
                                                                   const int32_t* __restrict__ long_rows, int rb_shift,
-                                                                  EpiArgs e) {
+                                                                  int spread, int n_rb_real, EpiArgs e) {
   __shared__ __align__(16) float s_part[(kStageThreads / 4) * 16];
   __shared__ int s_col[kSlabCap];
   __shared__ float s_val[kSlabCap];
@@ -391,10 +395,18 @@ __global__ void __launch_bounds__(kStageThreads, 6) k_gather_slab(GraphView g, c
   constexpr int G = kStageThreads / 4;
   const int bpc = n_rb + n_long;
   const int slab = blockIdx.x / bpc;
-  int b = blockIdx.x - slab * bpc;
-  if (b < n_rb) {
-    b += rb_shift;
-    if (b >= n_rb) b -= n_rb;
+  const int b0 = blockIdx.x - slab * bpc;
+  const bool row_block = b0 < n_rb;  // else: one of the long rows
+  int b = b0;
+  if (row_block) {
+    if (spread > 1) {
+      const int per = n_rb / spread;  // n_rb is a multiple of spread here
+      b = (b0 % spread) * per + (b0 / spread);
+      if (b >= n_rb_real) return;
+    } else {
+      b += rb_shift;
+      if (b >= n_rb) b -= n_rb;
+    }
   }
   const int sub = threadIdx.x & 3;
   const int gidx = threadIdx.x >> 2;
@@ -403,7 +415,7 @@ __global__ void __launch_bounds__(kStageThreads, 6) k_gather_slab(GraphView g, c
   auto emit = [&](int64_t row, const float4& v) {
     store_z_owner<4>(e.feat, e.feat_rank, hc_log2, (row << hc_log2) + slab * 16 + sub * 4, v.x, v.y, v.z, v.w);
   };
-  if (b < n_rb) {
+  if (row_block) {
     const int64_t r0 = (int64_t)b * kSlabRows;
     const int nr = (int)min((int64_t)kSlabRows, g.n_rows - r0);
     for (int i = threadIdx.x; i <= nr; i += kStageThreads) s_rp[i] = __ldg(g.rowptr + r0 + i);
@@ -450,7 +462,7 @@ __global__ void __launch_bounds__(kStageThreads, 6) k_gather_slab(GraphView g, c
       row = __shfl_sync(gmask, nxt, (threadIdx.x & 31) & ~3);
     }
   } else {
-    const int64_t row = __ldg(long_rows + (b - n_rb));
+    const int64_t row = __ldg(long_rows + (b0 - n_rb));
     const int start = __ldg(g.rowptr + row), end = __ldg(g.rowptr + row + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int idx = start + gidx; idx < end; idx += 4 * G) {

@@ -278,8 +278,10 @@ static int launch_ndcn_fast(const NdcnArgs& a, EpiArgs& e, int* grid_out, cudaSt
 template <int KIND>
 static int launch_dyn(const DynArgs& a, EpiArgs& e, double avg_deg, int* grid_out, cudaStream_t st) {
   const int64_t n = a.g.n_rows;
-  if (a.d == 1 && n >= 32768) {
-    // at scale: CSR-stream kernel (slice staged in shared memory, entry-parallel terms, CSR-order row sums)
+  if (a.d == 1 && n >= 32768 && KIND != NDCN_RHS_MUTUAL) {
+    // at scale: CSR-stream kernel (slice staged in shared memory, entry-parallel terms, CSR-order row sums).  Measured
+    // at 1M nodes, ms per dopri5 step: heat 1.89 -> 1.24, gene 1.97 -> 1.50, mutualistic 1.91 -> 2.60 (its per-entry
+    // term is division-heavy and gains nothing from the staging): the mutualistic RHS keeps the lane-group kernel
     const int grid = (int)((n + kDynRows - 1) / kDynRows) + a.n_long;
     *grid_out = grid;
     k_stage_dyn1_stream<KIND><<<grid, kStageThreads, 0, st>>>(a, e);
@@ -440,14 +442,15 @@ static int launch_umma(const UmmaArgs& u, EpiArgs& e, int sm_count, int* grid_ou
         case 0: NDCN_UMMA_CASE(EPI_LINCOMB, 0, 2, 1);
         case 1: NDCN_UMMA_CASE(EPI_LINCOMB, 1, 2, 1);
         case 2: NDCN_UMMA_CASE(EPI_LINCOMB, 2, 2, 1);
-        case 3: NDCN_UMMA_CASE(EPI_LINCOMB, 3, 1, 2);
-        case 4: NDCN_UMMA_CASE(EPI_LINCOMB, 4, 1, 2);
+        // batch depth 2 measured 2-5 % faster than 1 at 3-4 earlier stages in round 2 (ncu, profiles/README.md)
+        case 3: NDCN_UMMA_CASE(EPI_LINCOMB, 3, 2, 1);
+        case 4: NDCN_UMMA_CASE(EPI_LINCOMB, 4, 2, 1);
         case 5: NDCN_UMMA_CASE(EPI_LINCOMB, 5, 1, 2);
         default: return NDCN_E_ARG;
       }
     case EPI_LINCOMB_E:
       switch (e.n_prev) {
-        case 4: NDCN_UMMA_CASE(EPI_LINCOMB_E, 4, 1, 2);
+        case 4: NDCN_UMMA_CASE(EPI_LINCOMB_E, 4, 2, 1);
         case 5: NDCN_UMMA_CASE(EPI_LINCOMB_E, 5, 1, 2);
         default: return NDCN_E_ARG;
       }
@@ -1343,17 +1346,21 @@ struct Driver : StageTimer {
       int rcg = 0;
       if (sv->feat_slab) {
         const ndcn_graph* fg = sv->full_graph;
-        const int n_rb = (int)((fg->v.n_rows + kSlabRows - 1) / kSlabRows);
+        const int n_rb_real = (int)((fg->v.n_rows + kSlabRows - 1) / kSlabRows);
+        // NDCN_FEAT_SPREAD=1 (default): consecutive CTAs take row blocks of different owners, so that the CTAs resident
+        // at any moment store z to ALL ranks at once instead of all ranks storing to the same owner (k_gather_slab)
+        static const int spread_on = [] { const char* v = std::getenv("NDCN_FEAT_SPREAD"); return v ? std::atoi(v) : 1; }();
+        const int spread = spread_on ? sv->feat_world : 1;
+        const int n_rb = spread > 1 ? spread * ((n_rb_real + spread - 1) / spread) : n_rb_real;
         const int64_t grid = (int64_t)(sv->feat_hc / 16) * (n_rb + fg->n_long);
         sv->launches += 1;
-        // NDCN_FEAT_ROTATE=1: every rank starts the walk at its own row block, so that at any moment the ranks store z
-        // to different owners.  Measured on 8 / 4 B200s (profiles/README.md): 5.47 / 9.06 ms per step against
-        // 5.33 / 8.76 ms with the common start -- the hub-heavy first block desynchronises the ranks either way -- so off
+        // NDCN_FEAT_ROTATE=1 (with NDCN_FEAT_SPREAD=0): every rank starts the walk at its own row block.  Measured on
+        // 8 / 4 B200s (profiles/README.md): 5.47 / 9.06 ms per step against 5.33 / 8.76 ms with the common start
         int rb_shift = 0;
         if (const char* v = std::getenv("NDCN_FEAT_ROTATE"))
           if (std::atoi(v)) rb_shift = (int)((int64_t)sv->feat_bounds[sv->feat_rank] / kSlabRows);
         k_gather_slab<<<(unsigned)grid, kStageThreads, 0, st>>>(fg->v, sv->xcs_self, fg->v.n_cols, n_rb, fg->n_long, fg->long_rows,
-                                                                rb_shift % std::max(n_rb, 1), se);
+                                                                rb_shift % std::max(n_rb, 1), spread, n_rb_real, se);
         rcg = (int)cudaGetLastError();
       } else {
         rcg = launch_stage(bg, pp(sv->xcs_self), se, nullptr, st);

@@ -405,12 +405,9 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, int64_t off, const flo
       // stages are all clipped, and a zero numerator sends IEEE division down its slow path (measured:
       // ~15 % of the error-stage kernel's samples)
       float r = 0.f;
-#ifdef NDCN_ERR_FAST_DIV
-      // experiment (scripts/gpu_r2_l.sh): rcp + mul (2 ulp) instead of the IEEE division
-      if (acc[i] != 0.f) r = __fdividef(acc[i], tol);
-#else
+      // (an approximate division here was measured: 1.32 -> 1.25 ms for the error stage, not worth giving up the
+      // reference's IEEE quotient)
       if (acc[i] != 0.f) r = fdiv(acc[i], tol);
-#endif
       float r2 = fmul(r, r);
       // torch.max propagates NaN, fmaxf does not: keep the poison visible to the controller
       if (!(r2 == r2) || in.y0[i] != in.y0[i] || in.y1[i] != in.y1[i]) r2 = __int_as_float(0x7fc00000);
