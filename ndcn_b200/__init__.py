@@ -13,6 +13,8 @@ Layout
   partition.py     1-D row partition + halo exchange for multi-GPU solves
   shims/           modules named like the reference's (neural_dynamics, torchdiffeq)
   run.py           launcher: runs an unmodified reference script on this backend
+  workloads.py     sparse graph generators, operators and node orderings (host side, start-up only)
+  experiment.py    the dynamics scripts' experiment on sparse operators (100k - 4M nodes)
 """
 from .graph import CsrGraph, cached_graph
 from .solver import RhsSpec, SolveInfo, odeint_fused, rhs_eval, spmm

@@ -107,6 +107,74 @@ def grid_adjacency(side: int) -> sp.csr_matrix:
     return _symmetrize(np.concatenate(src), np.concatenate(dst), side * side)
 
 
+def small_world_adjacency(n: int, k: int = 5, p: float = 0.5, seed: int = 0) -> sp.csr_matrix:
+    """Newman-Watts-Strogatz graph (``nx.newman_watts_strogatz_graph(400, 5, 0.5)`` in the scripts,
+    heat_dynamics.py:99): a ring in which every node is linked to its k // 2 nearest neighbours on
+    either side, plus, for every ring edge, one extra shortcut from its first endpoint to a uniformly
+    drawn node with probability p.  (networkx re-draws a shortcut that hits an existing edge or the
+    node itself; here such a draw is dropped -- a fraction ~k/n of the shortcuts.)"""
+    assert n > k >= 2
+    rs = np.random.RandomState(seed)
+    u = np.arange(n, dtype=np.int64)
+    src = [u for _ in range(1, k // 2 + 1)]
+    dst = [(u + j) % n for j in range(1, k // 2 + 1)]
+    ring_src = np.concatenate(src)
+    add = rs.random_sample(len(ring_src)) < p
+    w = rs.randint(0, n, int(add.sum())).astype(np.int64)
+    src.append(ring_src[add])
+    dst.append(w)
+    return _symmetrize(np.concatenate(src), np.concatenate(dst), n)
+
+
+def community_adjacency(sizes, p_in: float = 0.25, p_out: float = 0.01, seed: int = 0) -> sp.csr_matrix:
+    """Planted-partition graph (``nx.random_partition_graph([n/3, n/3, n/4, rest], .25, .01)`` in
+    the scripts, heat_dynamics.py:104-109) without the N x N Bernoulli matrix: for every pair of
+    blocks the number of edges is drawn from its binomial law and that many node pairs are sampled
+    uniformly (duplicates collapse, a fraction ~p of them), nodes numbered block after block."""
+    rs = np.random.RandomState(seed)
+    sizes = [int(s) for s in sizes]
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    src, dst = [], []
+    for a in range(len(sizes)):
+        for b in range(a, len(sizes)):
+            pairs = sizes[a] * (sizes[a] - 1) // 2 if a == b else sizes[a] * sizes[b]
+            m = rs.binomial(pairs, p_in if a == b else p_out) if pairs else 0
+            if m == 0:
+                continue
+            src.append(start[a] + rs.randint(0, sizes[a], m).astype(np.int64))
+            dst.append(start[b] + rs.randint(0, sizes[b], m).astype(np.int64))
+    if not src:
+        return sp.csr_matrix((int(start[-1]), int(start[-1])), dtype=np.float32)
+    return _symmetrize(np.concatenate(src), np.concatenate(dst), int(start[-1]))
+
+
+def network(kind: str, n: int, seed: int = 0, mean_degree: float = None) -> sp.csr_matrix:
+    """The scripts' ``--network`` choices (heat_dynamics.py:83-110) at any size, sparse.
+
+    ``grid`` uses side = ceil(sqrt(n)) like the scripts (so the graph has side**2 >= n nodes);
+    ``random`` and ``community`` keep the scripts' edge probabilities (0.1; 0.25 / 0.01) unless
+    ``mean_degree`` is given, in which case the probabilities are scaled to that mean degree --
+    at 1M nodes p = 0.1 would be 5e10 edges."""
+    if kind == "grid":
+        return grid_adjacency(int(np.ceil(np.sqrt(n))))
+    if kind == "random":
+        return erdos_renyi_adjacency(n, 0.1 * (n - 1) if mean_degree is None else mean_degree, seed)
+    if kind == "power_law":
+        return power_law_adjacency(n, 5, seed)
+    if kind == "small_world":
+        return small_world_adjacency(n, 5, 0.5, seed)
+    if kind == "community":
+        n1, n2, n3 = n // 3, n // 3, n // 4
+        sizes = [n1, n2, n3, n - n1 - n2 - n3]
+        p_in, p_out = 0.25, 0.01
+        if mean_degree is not None:
+            # same in/out ratio of expected degrees as the scripts' 0.25 / 0.01 on four blocks
+            base = sum(s * (p_in * (s - 1) + p_out * (n - s)) for s in sizes) / n
+            p_in, p_out = p_in * mean_degree / base, p_out * mean_degree / base
+        return community_adjacency(sizes, p_in, p_out, seed)
+    raise ValueError("unknown network %r" % (kind,))
+
+
 def reorder_by_degree(a: sp.csr_matrix) -> Tuple[sp.csr_matrix, np.ndarray]:
     """``--layout degree`` (utils_in_learn_dynamics.py:212-247): nodes sorted by decreasing degree
     (stable).  Returns the permuted adjacency and ``perm`` with new_id = rank of old id."""

@@ -123,3 +123,91 @@ def test_generators_shapes_and_degree_law():
     assert 9.5 < np.asarray(e.sum(1)).mean() < 10.5
     g = wl.grid_adjacency(20)
     assert g.nnz == 2964  # grid_8_neighbor_graph(20), SURVEY.md section 3.1
+
+
+# ------------------------------------------------------------------------------------------
+# the scripts' --network choices without dense matrices (heat_dynamics.py:83-110)
+# ------------------------------------------------------------------------------------------
+def _is_simple_undirected(a):
+    d = a.toarray()
+    return (d == d.T).all() and d.diagonal().sum() == 0 and set(np.unique(d)) <= {0.0, 1.0}
+
+
+def test_small_world_ring_plus_shortcuts():
+    n, k, p = 3000, 5, 0.5
+    a = wl.small_world_adjacency(n, k, p, seed=1)
+    assert _is_simple_undirected(a)
+    d = a.toarray()
+    i = np.arange(n)
+    for j in (1, 2):  # the ring lattice is always there
+        assert (d[i, (i + j) % n] == 1).all()
+    ring = n * (k // 2)
+    extra = a.nnz // 2 - ring
+    # one Bernoulli(p) shortcut per ring edge, minus the few that hit an existing edge
+    assert abs(extra - p * ring) < 4 * np.sqrt(ring * p * (1 - p)) + 0.01 * ring
+    # networkx draws from the same law: same mean degree within sampling noise
+    nx = pytest.importorskip("networkx")
+    g = nx.newman_watts_strogatz_graph(n, k, p, seed=1)
+    assert abs(g.number_of_edges() - a.nnz // 2) < 0.03 * g.number_of_edges()
+
+
+def test_community_graph_block_densities():
+    sizes = [700, 700, 500, 200]
+    a = wl.community_adjacency(sizes, 0.25, 0.01, seed=2)
+    assert _is_simple_undirected(a) and a.shape[0] == sum(sizes)
+    d = a.toarray()
+    start = np.concatenate([[0], np.cumsum(sizes)])
+    for x in range(4):
+        for y in range(4):
+            blk = d[start[x]:start[x + 1], start[y]:start[y + 1]]
+            dens = blk.sum() / (sizes[x] * (sizes[x] - 1) if x == y else blk.size)
+            # pairs are sampled with replacement: the density is 1 - exp(-p) (~p - p^2/2)
+            want = 1 - np.exp(-(0.25 if x == y else 0.01))
+            assert abs(dens - want) < 0.06 * want + 1e-3, (x, y, dens, want)
+
+
+@pytest.mark.parametrize("kind", ["grid", "random", "power_law", "small_world", "community"])
+def test_network_dispatch_sizes_and_mean_degree(kind):
+    n = 900
+    a = wl.network(kind, n, seed=0)
+    assert a.shape == (n, n) and _is_simple_undirected(a)
+    if kind in ("random", "community"):
+        b = wl.network(kind, 20000, seed=0, mean_degree=12.0)
+        assert b.shape == (20000, 20000)
+        assert abs(b.nnz / 20000 - 12.0) < 0.5
+    with pytest.raises(ValueError):
+        wl.network("ring", n)
+
+
+def test_experiment_host_logic_follows_the_scripts():
+    """initial value and time sampling of the scale driver = the scripts' own statements
+    (heat_dynamics.py:119-151,178-183), re-evaluated here from the same numpy seed."""
+    import torch
+
+    from ndcn_b200 import experiment as ex
+
+    x0 = ex.initial_value(400)
+    ref = torch.zeros(20, 20)
+    ref[1:5, 1:5] = 25
+    ref[9:15, 9:15] = 20
+    ref[1:5, 7:13] = 17
+    assert torch.equal(x0, ref.view(-1, 1))
+    assert ex.initial_value(390).shape == (390, 1) and torch.equal(ex.initial_value(390), x0[:390])
+
+    t, tr, te, te2 = ex.time_ticks("equal", 5.0, 100)
+    assert torch.equal(t, torch.linspace(0.0, 5.0, 100)) and tr == list(range(80)) and te == list(range(80, 100))
+    assert te2 is None
+
+    np.random.seed(7)
+    t, tr, te, te2 = ex.time_ticks("irregular", 5.0, 100)
+    np.random.seed(7)
+    tt = torch.linspace(0.0, 5.0, 1000)
+    tt = torch.tensor(np.sort(np.random.permutation(tt)[:120]))
+    tt[0] = 0
+    want2 = sorted(np.random.permutation(range(1, 100))[:20].tolist())
+    assert torch.equal(t, tt) and te == list(range(100, 120)) and te2 == want2
+    assert tr == sorted(set(range(100)) - set(want2)) and len(tr) == 80
+    args = ex.parser().parse_args(["--network", "community", "--n", "1200", "--layout", "degree"])
+    a = ex.build_graph(args)
+    deg = np.diff(a.indptr)
+    assert a.shape == (1200, 1200) and (np.diff(deg) <= 0).all()
