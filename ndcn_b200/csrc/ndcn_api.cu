@@ -812,17 +812,33 @@ extern "C" int ndcn_weight_grads_f32(const float* gp, const float* z, int64_t n,
     }
     return NDCN_OK;
   }
-  const int tiles = (H + kWgTile - 1) / kWgTile;
+  // tensor-core tiles (128 x 128, mma.sync 3xTF32) for the wide layers, 64 x 64 FP32-FMA tiles otherwise
+  static const bool mma_on = [] { const char* e = std::getenv("NDCN_WG_MMA"); return !(e && e[0] == '0'); }();
+  const bool use_mma = mma_on && H % kWgmTile == 0 && n >= 1024 && aligned16(gp) && aligned16(z);
+  const int tile = use_mma ? kWgmTile : kWgTile, kstep = use_mma ? kWgmK : kWgK;
+  const int tiles = (H + tile - 1) / tile;
   // enough row chunks to fill the chip twice, at least 64 rows each
   int64_t nz = std::max<int64_t>(1, (2 * (int64_t)sm_count_now() + tiles * tiles - 1) / (tiles * tiles));
   nz = std::min<int64_t>(nz, (n + 63) / 64);
   int64_t rows_per_chunk = (n + nz - 1) / nz;
-  rows_per_chunk = (rows_per_chunk + kWgK - 1) / kWgK * kWgK;
+  rows_per_chunk = (rows_per_chunk + kstep - 1) / kstep * kstep;
   nz = (n + rows_per_chunk - 1) / rows_per_chunk;
+  if (use_mma) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
+      CU_TRY(cudaFuncSetAttribute(k_weight_grads_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgmSmemBytes));
+      attr.mark();
+    }
+  }
   float* part = nullptr;
   CU_TRY(cudaMallocAsync((void**)&part, sizeof(float) * (size_t)nz * (hh + H), st));
   float* part_b = db ? part + (size_t)nz * hh : nullptr;
-  k_weight_grads_partial<<<dim3(tiles, tiles, (unsigned)nz), 256, 0, st>>>(gp, z, n, H, rows_per_chunk, part, part_b);
+  if (use_mma) {
+    k_weight_grads_mma<<<dim3(tiles, tiles, (unsigned)nz), kWgmThreads, kWgmSmemBytes, st>>>(gp, z, n, H, rows_per_chunk, part,
+                                                                                   part_b);
+  } else {
+    k_weight_grads_partial<<<dim3(tiles, tiles, (unsigned)nz), 256, 0, st>>>(gp, z, n, H, rows_per_chunk, part, part_b);
+  }
   k_weight_grads_reduce<<<(unsigned)((hh + 255) / 256), 256, 0, st>>>(part, (int)nz, hh, dW, accumulate ? 1 : 0);
   if (db) k_weight_grads_reduce<<<(H + 255) / 256, 256, 0, st>>>(part_b, (int)nz, H, db, accumulate ? 1 : 0);
   cudaFreeAsync(part, st);

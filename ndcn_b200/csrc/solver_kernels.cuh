@@ -725,6 +725,147 @@ __global__ void __launch_bounds__(256) k_weight_grads_partial(const float* __res
     part_b[(size_t)blockIdx.z * H + o0 + threadIdx.x] = bsum;
 }
 
+// ---------------------------------------------------------------------------------------
+// The same partial products on the tensor cores for H % 128 == 0 (the widths of BASELINE configs 2-5):
+// 128x128 output tile per CTA, 16 warps of 32x32, K = 32 node rows per pipeline stage brought in by 16-byte
+// cp.async (two stages), mma.sync m16n8k8 tf32 with both operands split into tf32 hi + lo in registers and
+// lo*hi + hi*lo + hi*hi accumulated (3xTF32: the products keep ~21 mantissa bits).
+// The tensor core adds into its fp32 accumulator by TRUNCATION, a bias that grows with the length of the chain
+// (measured: relative error 1e-5 at 1 350 rows per CTA, 1e-4 at 13 500), so the MMA chain is restarted from zero
+// every stage (12 accumulations) and the stage's partial is added to the running sum with a rounded FADD.
+// Row pitch 136 floats: a fragment load touches rows t = 0..3 and columns g = 0..7 -> bank 8t + g, conflict-free.
+// The K dimension (node rows) is the slow index of both operands, so no tcgen05 K-major image exists for them
+// without a transposing producer; the legacy tensor path already takes this reduction from 0.79 ms (64x64
+// FP32-FMA tiles; cuBLAS SGEMM 0.48 ms) to under 0.3 ms at 100k x 256.
+// ---------------------------------------------------------------------------------------
+constexpr int kWgmTile = 128;
+constexpr int kWgmK = 32;
+constexpr int kWgmThreads = 512;
+constexpr int kWgmPitch = kWgmTile + 8;
+constexpr int kWgmStageFloats = 2 * kWgmK * kWgmPitch;
+constexpr int kWgmSmemBytes = 2 * kWgmStageFloats * (int)sizeof(float);
+
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// rows [r, r + 32) of the two 128-column operand tiles -> one pipeline stage; rows past r1 are zero-filled
+__device__ __forceinline__ void wgm_load_stage(float* stage, const float* __restrict__ gp, const float* __restrict__ z,
+                                               int H, int o0, int i0, int64_t r, int64_t r1) {
+  for (int v = threadIdx.x; v < 2 * kWgmK * (kWgmTile / 4); v += kWgmThreads) {
+    const int which = v / (kWgmK * (kWgmTile / 4));
+    const int w = v - which * (kWgmK * (kWgmTile / 4));
+    const int row = w / (kWgmTile / 4), c4 = w - row * (kWgmTile / 4);
+    float* dst = stage + which * (kWgmK * kWgmPitch) + row * kWgmPitch + c4 * 4;
+    const int64_t rr = r + row;
+    if (rr < r1) {
+      const float* src = (which ? z + rr * H + i0 : gp + rr * H + o0) + c4 * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kWgmThreads, 1) k_weight_grads_mma(const float* __restrict__ gp,
+                                                                     const float* __restrict__ z, int64_t n, int H,
+                                                                     int64_t rows_per_chunk,
+                                                                     float* __restrict__ part /* [nz][H][H] */,
+                                                                     float* __restrict__ part_b /* [nz][H] or null */) {
+  extern __shared__ __align__(16) float wgm_smem[];
+  const int o0 = blockIdx.y * kWgmTile, i0 = blockIdx.x * kWgmTile;
+  const int64_t r0 = (int64_t)blockIdx.z * rows_per_chunk;
+  const int64_t r1 = min(n, r0 + rows_per_chunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;  // the warp's 32 x 32 block of the tile
+  float sum[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sum[a][b][c] = 0.f;
+  float bsum = 0.f;
+  const bool want_b = part_b != nullptr && blockIdx.x == 0 && threadIdx.x < kWgmTile;
+  const int64_t n_it = r1 > r0 ? (r1 - r0 + kWgmK - 1) / kWgmK : 0;
+  if (n_it > 0) wgm_load_stage(wgm_smem, gp, z, H, o0, i0, r0, r1);
+  for (int64_t it = 0; it < n_it; ++it) {
+    float* cur = wgm_smem + (it & 1) * kWgmStageFloats;
+    if (it + 1 < n_it) {
+      wgm_load_stage(wgm_smem + ((it + 1) & 1) * kWgmStageFloats, gp, z, H, o0, i0, r0 + (it + 1) * kWgmK, r1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* As = cur;                       // [k][o]
+    const float* Bs = cur + kWgmK * kWgmPitch;  // [k][i]
+    float acc[2][4][4];  // this stage's 32 rows, chain restarted from zero
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < kWgmK; k0 += 8) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const float* p = As + (k0 + t) * kWgmPitch + wm + a * 16 + g;
+        tf32_split(p[0], ah[a][0], al[a][0]);
+        tf32_split(p[8], ah[a][1], al[a][1]);
+        tf32_split(p[4 * kWgmPitch], ah[a][2], al[a][2]);
+        tf32_split(p[4 * kWgmPitch + 8], ah[a][3], al[a][3]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float* p = Bs + (k0 + t) * kWgmPitch + wn + b * 8 + g;
+        uint32_t bh[2], bl[2];
+        tf32_split(p[0], bh[0], bl[0]);
+        tf32_split(p[4 * kWgmPitch], bh[1], bl[1]);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          mma_tf32_16x8x8(acc[a][b], al[a], bh);
+          mma_tf32_16x8x8(acc[a][b], ah[a], bl);
+          mma_tf32_16x8x8(acc[a][b], ah[a], bh);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sum[a][b][c] += acc[a][b][c];
+    if (want_b) {
+#pragma unroll
+      for (int k = 0; k < kWgmK; ++k) bsum += As[k * kWgmPitch + threadIdx.x];
+    }
+    __syncthreads();
+  }
+  float* dst = part + (size_t)blockIdx.z * H * H;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int o = o0 + wm + a * 16 + g, i = i0 + wn + b * 8 + 2 * t;
+      *reinterpret_cast<float2*>(dst + (size_t)o * H + i) = make_float2(sum[a][b][0], sum[a][b][1]);
+      *reinterpret_cast<float2*>(dst + (size_t)(o + 8) * H + i) = make_float2(sum[a][b][2], sum[a][b][3]);
+    }
+  if (want_b) part_b[(size_t)blockIdx.z * H + o0 + threadIdx.x] = bsum;
+}
+
 // out[j] (+)= sum_c part[c][j], chunks added in order
 __global__ void __launch_bounds__(256) k_weight_grads_reduce(const float* __restrict__ part, int nz, int64_t count,
                                                              float* __restrict__ out, int accumulate) {

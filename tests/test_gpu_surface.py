@@ -361,3 +361,32 @@ def test_variant_forward_is_not_replaced_by_the_fused_kernel(golden):
     torch.testing.assert_close(y.cpu(), ref, rtol=RTOL, atol=1e-5)
     # the package's own class is recognised, and so is the reference's own source (tests/test_gpu_scripts.py runs it)
     assert recognise(nb.ODEFunc(20, OM).cuda(), 20, torch.device("cuda")) is not None
+
+
+@pytest.mark.parametrize("n,H", [(777, 20), (1000, 256), (4097, 128), (100_003, 256), (20_000, 384), (1_000_000, 256)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_weight_grads_kernels_vs_float64(n, H, accumulate):
+    """dW (+)= gp^T z, db (+)= column sums of gp (what autograd records through nn.Linear, neural_dynamics.py:33)
+    on the library's reduction kernels: 64x64 FP32-FMA tiles, and for H % 128 == 0 and >= 1024 rows the
+    mma.sync 3xTF32 tiles (rows not a multiple of the 32-row pipeline stage, H = 3 x 128 tiles).  Bar: relative L2
+    error against float64 <= 3e-6 (fp32 row sums; 3xTF32 products keep ~21 mantissa bits; the tensor-core
+    accumulation chain is restarted every 32 rows because it truncates -- 1e-4 at 1M rows otherwise)."""
+    from ndcn_b200 import solver
+
+    g = torch.Generator().manual_seed(n + H)
+    gp = torch.randn(n, H, generator=g)
+    gp[torch.rand(n, H, generator=g) < 0.5] = 0.0  # a ReLU mask's zeros
+    z = torch.randn(n, H, generator=g) * 3.0
+    dW0 = torch.randn(H, H, generator=g)
+    db0 = torch.randn(H, generator=g)
+    dW, db = dW0.clone().cuda(), db0.clone().cuda()
+    solver.weight_grads(gp.cuda(), z.cuda(), dW, db, accumulate=accumulate)
+    want_W = gp.double().t() @ z.double() + (dW0.double() if accumulate else 0.0)
+    want_b = gp.double().sum(0) + (db0.double() if accumulate else 0.0)
+    err_W = float((dW.cpu().double() - want_W).norm() / want_W.norm())
+    err_b = float((db.cpu().double() - want_b).norm() / want_b.norm())
+    assert err_W <= 3e-6 and err_b <= 3e-6, (err_W, err_b)
+    # db = None: only dW is formed
+    dW2 = torch.zeros(H, H, device="cuda")
+    solver.weight_grads(gp.cuda(), z.cuda(), dW2, None, accumulate=False)
+    assert float((dW2.cpu().double() - gp.double().t() @ z.double()).norm() / want_W.norm()) <= 3e-6
