@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .odeint import odeint as _odeint
+from .odeint import odeint as _odeint, odeint_adjoint as _odeint_adjoint
 from . import solver as _solver
 from .autograd_solver import RhsFn, SpmmFn
 from .graph import cached_graph, require_cuda
@@ -111,8 +111,9 @@ class ODEBlock(nn.Module):
         """``decoder=(W, b)``: extension used by ``NDCN.forward`` -- the output Linear is applied to every
         returned state inside the solve (no ``[T, N, H]`` slab)."""
         integration_time_vector = vt.type_as(x)  # rounds the grid to the state's dtype FIRST (:71)
-        return _odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
-                           method=self.method, terminal_only=bool(self.terminal), decoder=decoder)
+        solve = _odeint_adjoint if self.adjoint else _odeint  # :72-78
+        return solve(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
+                     method=self.method, terminal_only=bool(self.terminal), decoder=decoder)
 
 
 class ODEBlock2(nn.Module):
@@ -130,8 +131,9 @@ class ODEBlock2(nn.Module):
 
     def forward(self, x):
         integration_time_vector = self.integration_time_vector.type_as(x)
-        return _odeint(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
-                           method=self.method, terminal_only=bool(self.terminal))
+        solve = _odeint_adjoint if self.adjoint else _odeint  # :111-118
+        return solve(self.odefunc, x, integration_time_vector, rtol=self.rtol, atol=self.atol,
+                     method=self.method, terminal_only=bool(self.terminal))
 
 
 class NDCN(nn.Module):

@@ -276,8 +276,24 @@ def _fixed_grid_and_picks(func, y0, t, step_size, grid_constructor):
     return grid, torch.tensor(picks, dtype=torch.long)
 
 
-def odeint_adjoint(func, y0, t, rtol=1e-6, atol=1e-12, method=None, options=None):
-    """Signature of torchdiffeq/_impl/adjoint.py:105.  No script of the reference enables the
-    adjoint (SURVEY.md section 2, row "Adjoint backward"); gradients are obtained by
-    backpropagating through the solver instead of re-solving the augmented system."""
-    return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+_ADJOINT_NOTE_GIVEN = False
+
+
+def odeint_adjoint(func, y0, t, rtol=1e-6, atol=1e-12, method=None, options=None, **extensions):
+    """Signature, defaults and argument check of torchdiffeq/_impl/adjoint.py:105-111.  No script of the reference
+    enables the adjoint (SURVEY.md section 2, row "Adjoint backward").  The forward values are those of ``odeint``;
+    gradients are obtained by back-propagating through the solver's own steps (the discrete adjoint) instead of
+    re-solving the augmented system backwards in time (adjoint.py:7-102) -- the two agree up to the solver's
+    discretisation error, and a note says so once per process when gradients are enabled.  ``extensions`` are the
+    keyword-only extensions of ``odeint`` (``terminal_only``, ``decoder``)."""
+    global _ADJOINT_NOTE_GIVEN
+    if not isinstance(func, torch.nn.Module):
+        raise ValueError('func is required to be an instance of nn.Module.')
+    if torch.is_grad_enabled() and not _ADJOINT_NOTE_GIVEN:
+        import warnings
+
+        _ADJOINT_NOTE_GIVEN = True
+        warnings.warn("ndcn_b200.odeint_adjoint: gradients come from back-propagation through the solver steps "
+                      "(discrete adjoint), not from a backward solve of the augmented system; forward values are "
+                      "identical to odeint's")
+    return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options, **extensions)

@@ -390,3 +390,39 @@ def test_weight_grads_kernels_vs_float64(n, H, accumulate):
     dW2 = torch.zeros(H, H, device="cuda")
     solver.weight_grads(gp.cuda(), z.cuda(), dW2, None, accumulate=False)
     assert float((dW2.cpu().double() - gp.double().t() @ z.double()).norm() / want_W.norm()) <= 3e-6
+
+
+def test_odeblock_adjoint_flag_goes_through_odeint_adjoint(golden):
+    """neural_dynamics.py:72-78,111-118: ``adjoint=True`` solves through ``odeint_adjoint``.  Here that is the same
+    forward solve (bit-identical output) and gradients by back-propagation through the steps, announced once."""
+    import warnings
+
+    import ndcn_b200 as nb
+    from ndcn_b200 import odeint as odeint_mod
+
+    g = golden("cora_block")
+    adj = csr_to_coo(g, "adj_a00").cuda()
+    x = torch.from_numpy(np.tanh(np.random.RandomState(11).standard_normal((2708, 32))).astype(np.float32)).cuda()
+    vt = torch.linspace(0, 1.2, 16).float()
+    outs = []
+    for adjoint in (False, True):
+        torch.manual_seed(0)
+        fn = nb.ODEFunc(32, adj, dropout=0.0)
+        blk = nb.ODEBlock2(fn, vt, rtol=.1, atol=.1, method="dopri5", adjoint=adjoint, terminal=True).cuda()
+        with torch.no_grad():
+            outs.append(blk(x))
+    assert torch.equal(outs[0], outs[1])
+    # with gradients: one note per process, gradients equal to the non-adjoint block's
+    grads = []
+    odeint_mod._ADJOINT_NOTE_GIVEN = False
+    for adjoint in (False, True):
+        torch.manual_seed(0)
+        fn = nb.ODEFunc(32, adj, dropout=0.0)
+        blk = nb.ODEBlock(fn, rtol=.1, atol=.1, method="rk4", adjoint=adjoint, terminal=True).cuda()
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            blk(vt[:4].cuda(), x).square().sum().backward()
+            blk(vt[:4].cuda(), x)
+        assert sum("odeint_adjoint" in str(w.message) for w in rec) == (1 if adjoint else 0)
+        grads.append(fn.wt.weight.grad.clone())
+    torch.testing.assert_close(grads[0], grads[1], rtol=0, atol=0)

@@ -26,6 +26,12 @@ def test_surface_signatures_match_reference():
     assert pa["rtol"].default == 1e-6 and pa["atol"].default == 1e-12
 
 
+def test_odeint_adjoint_argument_check_matches_reference():
+    """adjoint.py:109-110: a plain callable is refused before anything else happens"""
+    with pytest.raises(ValueError, match="func is required to be an instance of nn.Module"):
+        nb.odeint_adjoint(lambda t, y: y, torch.ones(2, 2), torch.tensor([0.0, 1.0]))
+
+
 def test_state_dict_keys():
     m = nb.NDCN(1, 20, torch.eye(4), 1)
     assert sorted(m.state_dict()) == sorted([
