@@ -27,6 +27,50 @@ SOLVER_NAMES = ("explicit_adams", "fixed_adams", "adams", "tsit5", "dopri5", "eu
 FUSED_METHODS = ("euler", "midpoint", "rk4", "dopri5")
 
 
+# Solvers and state shapes outside the accelerated path (tsit5, the Adams family, tuple states of several tensors --
+# "OUT OF SCOPE -- keep as pure-PyTorch fallback").  The launcher (run.install) registers the
+# script's OWN vendored torchdiffeq here, loaded under a private module name, and such calls are handed to it
+# unchanged; they then run as eager PyTorch ops on whatever device the tensors live on.  Without a registered
+# package (library use without the reference on disk) those calls raise NotImplementedError.
+_OUT_OF_SCOPE_SOLVER = None
+
+
+def register_out_of_scope_solver(package_dir: Optional[str]) -> bool:
+    """``package_dir``: a directory holding the reference's ``torchdiffeq/__init__.py`` (or None to clear)."""
+    global _OUT_OF_SCOPE_SOLVER
+    _OUT_OF_SCOPE_SOLVER = None
+    if package_dir is None:
+        return False
+    import importlib.util
+    import os
+    import sys
+
+    init = os.path.join(package_dir, "torchdiffeq", "__init__.py")
+    if not os.path.isfile(init):
+        return False
+    name = "_ndcn_b200_script_torchdiffeq"
+    for key in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
+        del sys.modules[key]
+    spec = importlib.util.spec_from_file_location(name, init, submodule_search_locations=[os.path.dirname(init)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    try:
+        spec.loader.exec_module(mod)
+    except Exception:
+        del sys.modules[name]
+        return False
+    _OUT_OF_SCOPE_SOLVER = mod
+    return True
+
+
+def _delegate(what: str, func, y0, t, rtol, atol, method, options):
+    if _OUT_OF_SCOPE_SOLVER is None:
+        raise NotImplementedError("ndcn_b200 implements euler | midpoint | rk4 | dopri5 on single-tensor states (the "
+                                  "benchmarked path); %s is out of scope and no torchdiffeq package of the calling "
+                                  "script is registered to take it (ndcn_b200.run registers the script's own)" % what)
+    return _OUT_OF_SCOPE_SOLVER.odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+
+
 def _is_number(v) -> bool:
     return isinstance(v, (int, float)) and not isinstance(v, bool)
 
@@ -133,14 +177,14 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
     solve and the ``[T, N, H]`` slab is never written.
     """
     tuple_input = False
+    asked = (func, y0, options)  # what an out-of-scope call is handed on with
     if not torch.is_tensor(y0):
         # misc.py:173-183
         assert isinstance(y0, tuple), "y0 must be either a torch.Tensor or a tuple"
         for y0_ in y0:
             assert torch.is_tensor(y0_), "each element must be a torch.Tensor but received {}".format(type(y0_))
         if len(y0) != 1:
-            raise NotImplementedError("ndcn_b200.odeint: tuple states with more than one tensor are outside the "
-                                      "accelerated path (only torchdiffeq's adjoint uses them)")
+            return _delegate("a tuple state of %d tensors" % len(y0), func, y0, t, rtol, atol, method, options)
         tuple_input = True
         inner = func
         func = lambda tt, yy: inner(tt, (yy,))[0]  # noqa: E731
@@ -154,8 +198,9 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
     if method not in SOLVER_NAMES:
         raise KeyError(method)  # SOLVERS[method] in the reference (odeint.py:71)
     if method not in FUSED_METHODS:
-        raise NotImplementedError("ndcn_b200 implements euler | midpoint | rk4 | dopri5 (the methods on the "
-                                  "benchmarked path); %r is out of scope" % (method,))
+        if decoder is not None or terminal_only:
+            raise NotImplementedError("terminal_only / decoder are extensions of the accelerated methods")
+        return _delegate("method %r" % (method,), asked[0], asked[1], t, rtol, atol, method, asked[2])
     if not torch.is_floating_point(y0):
         raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y0.type()))
     if not torch.is_floating_point(t):

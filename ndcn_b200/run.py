@@ -63,6 +63,10 @@ def install(script_dir: str) -> None:
         sys.path.insert(0, p)
     for name in [n for n in sys.modules if n == "neural_dynamics" or n == "torchdiffeq" or n.startswith("torchdiffeq.")]:
         del sys.modules[name]
+    # solvers outside the accelerated path (--method tsit5 | adams | ...) are handed to the script's own torchdiffeq
+    import importlib
+
+    importlib.import_module("ndcn_b200.odeint").register_out_of_scope_solver(script_dir)  # the package re-exports the function under that name
 
 
 def run_script(argv, seed=None, run_name="__main__"):

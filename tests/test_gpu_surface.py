@@ -397,9 +397,11 @@ def test_odeblock_adjoint_flag_goes_through_odeint_adjoint(golden):
     forward solve (bit-identical output) and gradients by back-propagation through the steps, announced once."""
     import warnings
 
-    import ndcn_b200 as nb
-    from ndcn_b200 import odeint as odeint_mod
+    import importlib
 
+    import ndcn_b200 as nb
+
+    odeint_mod = importlib.import_module("ndcn_b200.odeint")  # the package re-exports the function under that name
     g = golden("cora_block")
     adj = csr_to_coo(g, "adj_a00").cuda()
     x = torch.from_numpy(np.tanh(np.random.RandomState(11).standard_normal((2708, 32))).astype(np.float32)).cuda()

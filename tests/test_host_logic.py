@@ -115,3 +115,38 @@ def test_bench_exchange_rule():
     assert bench.pick_exchange({"halo": 190e6, "push": 192e6, "feature": None}, 4, 64) == "push"
     # H / world below 32 columns: no feature-sharded push
     assert bench.pick_exchange({"halo": 428e6, "push": 448e6, "feature": None}, 8, 128) in ("push", "halo")
+
+
+def test_out_of_scope_solvers_are_handed_to_the_scripts_own_torchdiffeq():
+    """SURVEY.md section 2 "Other solvers": adams / fixed_adams / explicit_adams / tsit5 and tuple states of several
+    tensors are not accelerated.  Without a registered package they raise; under the launcher (run.install) the
+    script's own vendored torchdiffeq takes them unchanged (torchdiffeq/_impl/odeint.py:20-76)."""
+    import importlib
+    import os
+
+    om = importlib.import_module("ndcn_b200.odeint")
+    f = lambda t, y: -y  # noqa: E731
+    y0, t = torch.ones(3, 2), torch.linspace(0, 1, 5)
+    om.register_out_of_scope_solver(None)
+    with pytest.raises(NotImplementedError, match="out of scope"):
+        nb.odeint(f, y0, t, method="adams")
+    with pytest.raises(NotImplementedError, match="tuple state of 2 tensors"):
+        nb.odeint(lambda t, y: (-y[0], y[0]), (y0, y0), t)
+    with pytest.raises(KeyError):
+        nb.odeint(f, y0, t, method="rk45")
+    ref_dir = next((d for d in ("/root/reference", os.path.join(os.path.dirname(os.path.dirname(__file__)), "baseline", "_ref"))
+                    if os.path.isfile(os.path.join(d, "torchdiffeq", "__init__.py"))), None)
+    if ref_dir is None:
+        pytest.skip("no copy of the reference's torchdiffeq on this machine")
+    assert not om.register_out_of_scope_solver(os.path.dirname(__file__))  # no torchdiffeq there
+    assert om.register_out_of_scope_solver(ref_dir)
+    try:
+        theirs = om._OUT_OF_SCOPE_SOLVER
+        for method in ("adams", "explicit_adams"):
+            assert torch.equal(nb.odeint(f, y0, t, method=method), theirs.odeint(f, y0, t, method=method))
+        g = lambda t, y: (-y[0], y[0])  # noqa: E731
+        ours = nb.odeint(g, (y0, torch.zeros(3, 2)), t, rtol=1e-5, atol=1e-7, method="dopri5")
+        want = theirs.odeint(g, (y0, torch.zeros(3, 2)), t, rtol=1e-5, atol=1e-7, method="dopri5")
+        assert isinstance(ours, tuple) and all(torch.equal(a, b) for a, b in zip(ours, want))
+    finally:
+        om.register_out_of_scope_solver(None)
