@@ -118,6 +118,7 @@ static const double kDpBeta[6][6] = {
     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
     {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
 };
+static const double kDpAlpha[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};  // stage times, dopri5.py:12
 static const double kDpErr[7] = {
     35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
     -2187.0 / 6784 - -12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60.0,
@@ -1324,6 +1325,16 @@ struct Driver : StageTimer {
     return 0;
   }
 
+  // time of the next RHS evaluation, for a callback RHS (k_stage_time); the built-in right-hand sides are autonomous
+  int tm_mode = 0, tm_from_ctrl = 0;
+  float tm_base = 0.f, tm_dt = 0.f, tm_alpha = 0.f, tm_num = 0.f, tm_den = 1.f;
+  void time_host(float t0, float dt, int mode, float a = 0.f, float num = 0.f, float den = 1.f) {
+    tm_from_ctrl = 0; tm_base = t0; tm_dt = dt; tm_mode = mode; tm_alpha = a; tm_num = num; tm_den = den;
+  }
+  void time_ctrl(int mode, float a = 0.f, float base = 0.f) {
+    tm_from_ctrl = mode == 3 ? 0 : 1; tm_mode = mode; tm_alpha = a; tm_base = base; tm_dt = 0.f; tm_num = 0.f; tm_den = 1.f;
+  }
+
   // one RHS evaluation fused with epilogue e. `src_host` is the buffer the host knows to be the
   // source (needed for the exchange/callback hooks; the kernels themselves select by parity).
   int stage(PtrPair src, float* src_host, EpiArgs e, float* k_host, int* n_partials = nullptr) {
@@ -1392,6 +1403,9 @@ struct Driver : StageTimer {
     nfe += 1;
     if (sv->rhs.kind == NDCN_RHS_CALLBACK) {
       if (!sv->rhs.callback || !k_host) return NDCN_E_ARG;
+      sv->launches += 1;
+      k_stage_time<<<1, 1, 0, st>>>(sv->ctrl, tm_from_ctrl, tm_base, tm_dt, tm_alpha, tm_num, tm_den, tm_mode, sv->t_stage);
+      CU_TRY(cudaGetLastError());
       RC_TRY(sv->rhs.callback(sv->rhs.callback_user, src_host, k_host, sv->t_stage));
       // epilogue on the k the callback produced; k is already where it belongs
       EpiArgs e2 = e;
@@ -1468,34 +1482,41 @@ int run_fixed_grid(Driver& d, const float* y0, const double* t, int n_t, float* 
       e.mode = EPI_LINCOMB;
       e.beta[0] = 1.0f;
       e.y_out = pp(nxt);
+      d.time_host(t0, dt, 0);
       RC_TRY(d.stage(pp(cur), cur, e, sv->K[0]));
     } else if (sv->method == NDCN_MIDPOINT) {  // fixed_grid.py:17-20
       e.mode = EPI_LINCOMB;
       e.beta[0] = 0.5f;  // y + f*dt/2 == y + (dt*0.5)*f bit for bit (power-of-two scaling)
       e.y_out = pp(sv->YS[0]);
+      d.time_host(t0, dt, 0);
       RC_TRY(d.stage(pp(cur), cur, e, sv->K[0]));
       e.beta[0] = 1.0f;
       e.y_out = pp(nxt);
+      d.time_host(t0, dt, 2, 0.f, 1.f, 2.f);  // t + dt / 2
       RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[0]));
     } else {  // rk_common.py:72-78
       e.mode = EPI_RK4_1;
       e.k_out = pp(sv->K[0]);
       e.y_out = pp(sv->YS[0]);
+      d.time_host(t0, dt, 0);
       RC_TRY(d.stage(pp(cur), cur, e, sv->K[0]));
       e.mode = EPI_RK4_2;
       e.k_out = pp(sv->K[1]);
       e.kprev[0] = pp(sv->K[0]);
       e.y_out = pp(sv->YS[1]);
+      d.time_host(t0, dt, 2, 0.f, 1.f, 3.f);  // t + dt / 3
       RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[1]));
       e.mode = EPI_RK4_3;
       e.k_out = pp(sv->K[2]);
       e.kprev[1] = pp(sv->K[1]);
       e.y_out = pp(sv->YS[0]);
+      d.time_host(t0, dt, 2, 0.f, 2.f, 3.f);  // t + dt * 2 / 3
       RC_TRY(d.stage(pp(sv->YS[1]), sv->YS[1], e, sv->K[2]));
       e.mode = EPI_RK4_4;
       e.k_out = pp(nullptr);
       e.kprev[2] = pp(sv->K[2]);
       e.y_out = pp(nxt);
+      d.time_host(t0, dt, 1, 1.f);  // t + dt
       RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], e, sv->K[3]));
     }
     if (!in_slab && !terminal) RC_TRY(d.put_state(out, i + 1, nxt));
@@ -1539,6 +1560,7 @@ struct Dopri {
   ndcn_solver* sv;
   float beta32[6][8];
   float err32[8];
+  float alpha32[6];
   EmitArgs emit;
   bool host_parity;  // hooks need the host to know the buffer parity: poll every attempt
   int par = 0;
@@ -1550,6 +1572,7 @@ struct Dopri {
     for (int s = 0; s < 6; ++s)
       for (int j = 0; j <= s; ++j) beta32[s][j] = (float)kDpBeta[s][j];
     for (int j = 0; j < 7; ++j) err32[j] = (float)kDpErr[j];
+    for (int j = 0; j < 6; ++j) alpha32[j] = (float)kDpAlpha[j];
     if (const char* v = std::getenv("NDCN_ERR_PREFIX")) err_prefix = std::atoi(v) != 0;
   }
 
@@ -1601,6 +1624,7 @@ struct Dopri {
         e.e_out = sv->YS[1];
         for (int j = 0; j < 8; ++j) e.ebeta[j] = j < 6 ? err32[j] : 0.0f;
       }
+      d.time_ctrl(1, alpha32[s - 1]);
       RC_TRY(d.stage(pp(src), src, e, sv->K[s - 1]));
     }
     // stage 6: k7 = f(y1) + error estimate
@@ -1623,6 +1647,7 @@ struct Dopri {
     e.rtol = (float)d.o->rtol;
     e.atol = (float)d.o->atol;
     int n_partials = 0;
+    d.time_ctrl(1, alpha32[5]);
     RC_TRY(d.stage(Yoth, Yq, e, KFq, &n_partials));
     RC_TRY(reduce_and_control(n_partials));
     sv->launches += 1;
@@ -1707,6 +1732,7 @@ struct Dopri {
     emit.n_rows = sv->n_rows;
 
     // f0 = func(t0, y0)     dopri5.py:78
+    d.time_host((float)t[0], 0.f, 0);
     RC_TRY(d.stage(pp(sv->Y[0]), sv->Y[0], store_only(sv->KF[0]), sv->KF[0]));
     if (!forced && !given_first) {
       // _select_initial_step(order=4)     dopri5.py:80, misc.py:84-143
@@ -1724,6 +1750,7 @@ struct Dopri {
       e.y0 = pp(sv->Y[0]);
       e.y_out = pp(sv->YS[0]);
       RC_TRY(d.epi_only(pp(sv->KF[0]), e));  // y0 + h0*f0
+      d.time_ctrl(3, 0.f, (float)t[0]);      // func(t0 + h0, .), misc.py:126
       RC_TRY(d.stage(pp(sv->YS[0]), sv->YS[0], store_only(sv->K[0]), sv->K[0]));
       sv->launches += 1;
       k_init_norms<<<grid, kStageThreads, 0, st>>>(sv->Y[0], sv->KF[0], sv->K[0], sv->numel, (float)d.o->rtol,

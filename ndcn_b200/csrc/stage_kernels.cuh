@@ -723,18 +723,24 @@ __global__ void __launch_bounds__(kStageThreads) k_epi_only(PtrPair k_in, int64_
   epi_finish_block(e, err_acc);
 }
 
-// fp32 stage time handed to a callback RHS: rk_common.py:49 (t0 + alpha*dt, fp32),
-// fixed_grid.py / rk_common.py:72-78 (t + dt*num/den)
-__global__ void k_stage_time(const Ctrl* ctrl, float base, float dt_host, float alpha, float num, float den, int mode,
-                             float* t_stage) {
+// fp32 stage time handed to a callback RHS (the reference converts t0 and dt to the state's dtype before it forms
+// the stage times, rk_common.py:44-49):
+//   mode 0  t0                      func(t, y) of every first stage; dopri5.py:78
+//   mode 1  t0 + alpha*dt           rk_common.py:49; rk_common.py:78 (alpha = 1)
+//   mode 2  t0 + (dt*num)/den       fixed_grid.py:20 (dt/2), rk_common.py:75-76 (dt/3, dt*2/3)
+//   mode 3  base + h0 in float64    the probe of _select_initial_step, misc.py:126 (t0 is float64 there)
+// from_ctrl: t0 / dt are the adaptive solver's current time and step (Ctrl::t1, Ctrl::dt) instead of host values.
+__global__ void k_stage_time(const Ctrl* ctrl, int from_ctrl, float base, float dt_host, float alpha, float num,
+                             float den, int mode, float* t_stage) {
   float t0 = base, dt = dt_host;
-  if (ctrl != nullptr) {
+  if (from_ctrl) {
     t0 = (float)ctrl->t1;
     dt = (float)ctrl->dt;
   }
   if (mode == 0) *t_stage = t0;
   else if (mode == 1) *t_stage = fadd(t0, fmul(alpha, dt));
-  else *t_stage = fadd(t0, fdiv(fmul(dt, num), den));
+  else if (mode == 2) *t_stage = fadd(t0, fdiv(fmul(dt, num), den));
+  else *t_stage = (float)((double)base + (double)ctrl->h0);
 }
 
 }  // namespace ndcn

@@ -15,6 +15,7 @@ Dispatch
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -266,6 +267,11 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
                 out.copy_(res)
             else:
                 out = res.to(y0.device)
+        elif y0.is_cuda and os.environ.get("NDCN_GENERIC_FUSED", "1") != "0":
+            # any other callable on a CUDA state: the solver algebra (stage combinations, error norm, step-size
+            # controller, dense output) stays on the library's kernels and only the RHS is func itself
+            out = _solve_callable_fused(func, y0.detach(), t, method, float(rtol), float(atol), terminal_only,
+                                        max_num_steps, fused_kw)
     if (out is None and y0.is_cuda and y0.dim() == 2 and y0.dtype == torch.float32 and method in ("euler", "midpoint", "rk4")
             and type(func).__name__ == "ODEFunc" and hasattr(func, "wt") and getattr(func.wt, "bias", None) is not None
             and not (getattr(func, "dropout", 0.0) and getattr(func, "training", False))):
@@ -290,6 +296,48 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, *, term
     if decoder is not None:
         out = torch.nn.functional.linear(out, decoder[0].to(out.device), None if decoder[1] is None else decoder[1].to(out.device))
     return (out,) if tuple_input else out
+
+
+class _DeviceArray:
+    """A device pointer the library hands to a callback, dressed for ``torch.as_tensor`` (no copy)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _solve_callable_fused(func, y0, t, method, rtol, atol, terminal_only, max_num_steps, fused_kw):
+    """``odeint`` of an arbitrary ``func(t, y)`` (odeint.py:20) on an fp32 ``[N, d]`` CUDA state through
+    ``NDCN_RHS_CALLBACK``: every RHS evaluation calls back into Python with views of the solver's own stage-input and
+    k buffers and the fp32 stage time as a 0-dim device tensor (rk_common.py:44-49); func runs under ``no_grad`` on
+    the solver's stream, nothing is synchronised for a fixed grid and once per attempted step for dopri5."""
+    from . import _ffi
+    from .models import _identity_graph
+
+    dev = y0.device
+    n, d = int(y0.shape[0]), int(y0.shape[1])
+    failure = []
+
+    def rhs(_user, y_ptr, k_ptr, t_ptr):
+        try:
+            y = torch.as_tensor(_DeviceArray(y_ptr, (n, d)), device=dev)
+            k = torch.as_tensor(_DeviceArray(k_ptr, (n, d)), device=dev)
+            tt = torch.as_tensor(_DeviceArray(t_ptr, (1,)), device=dev)[0]
+            with torch.no_grad():
+                k.copy_(func(tt, y).reshape(n, d))
+            return 0
+        except BaseException as exc:  # must not unwind through the C frames
+            failure.append(exc)
+            return _ffi.E_ARG
+
+    spec = RhsSpec(_ffi.RHS_CALLBACK_KIND, d, callback=rhs)
+    try:
+        return solver.odeint_fused(_identity_graph(n, dev), spec, y0.contiguous(), t, method=method, rtol=rtol,
+                                   atol=atol, terminal_only=terminal_only, max_num_steps=max_num_steps, **fused_kw)
+    except Exception:
+        if failure:
+            raise failure[0]
+        raise
 
 
 def _fixed_grid_and_picks(func, y0, t, step_size, grid_constructor):

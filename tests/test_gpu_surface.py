@@ -428,3 +428,65 @@ def test_odeblock_adjoint_flag_goes_through_odeint_adjoint(golden):
         assert sum("odeint_adjoint" in str(w.message) for w in rec) == (1 if adjoint else 0)
         grads.append(fn.wt.weight.grad.clone())
     torch.testing.assert_close(grads[0], grads[1], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4", "dopri5"])
+def test_generic_callable_takes_the_fused_solver_algebra(method):
+    """Any func(t, y) (odeint.py:20) on an fp32 [N, d] CUDA state: the RHS is the callable itself (NDCN_RHS_CALLBACK),
+    everything else -- stage combinations, error norm, controller, dense output -- the library's kernels.  A
+    TIME-DEPENDENT, non-linear func checks the stage times the callback is given (rk_common.py:49,72-78,
+    fixed_grid.py:17-20, dopri5.py:78, misc.py:126) and the adaptive step sequence against the oracle."""
+    import ndcn_b200 as nb
+    from ndcn_b200 import solver
+
+    n, d = 700, 12
+    g = torch.Generator().manual_seed(3)
+    y0 = torch.randn(n, d, generator=g)
+    A = torch.randn(d, d, generator=g) * 0.3
+    t = torch.tensor([0.0, 0.13, 0.5, 0.51, 1.2])
+    calls = []
+
+    def make(dev):
+        Ad = A.to(dev)
+
+        def f(tt, y):
+            calls.append((tt.dtype, tt.dim(), tuple(y.shape)))
+            return torch.tanh(y @ Ad) * torch.cos(3.0 * tt) - 0.5 * tt * y
+        return f
+
+    solver.last_solve_info = None
+    out = nb.odeint(make("cuda"), y0.cuda(), t.cuda(), rtol=1e-5, atol=1e-7, method=method)
+    info = solver.last_solve_info
+    assert info is not None and info.nfe > 0, "the fused solver did not run"
+    assert calls and all(c == (torch.float32, 0, (n, d)) for c in calls)
+    n_gpu = len(calls)
+    assert info.nfe == n_gpu
+    calls.clear()
+    stats = O.SolveStats()
+    ref = O.odeint(make("cpu"), y0, t, rtol=1e-5, atol=1e-7, method=method, stats=stats)
+    assert stats.nfe == n_gpu == len(calls)
+    if method == "dopri5":
+        assert (info.n_accepted, info.n_rejected) == (stats.n_accepted, stats.n_rejected)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=2e-6)
+
+
+def test_generic_callable_errors_and_escape_hatch(monkeypatch):
+    import ndcn_b200 as nb
+    from ndcn_b200 import solver
+
+    y0 = torch.ones(64, 4).cuda()
+    t = torch.linspace(0, 1, 4).cuda()
+
+    def broken(tt, y):
+        raise ZeroDivisionError("inside the user's func")
+
+    with pytest.raises(ZeroDivisionError, match="inside the user's func"):
+        nb.odeint(broken, y0, t, method="rk4")
+    # the library is usable afterwards, and NDCN_GENERIC_FUSED=0 takes the op-by-op path with the same result
+    f = lambda tt, y: -y * (1.0 + tt)  # noqa: E731
+    a = nb.odeint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-8)
+    solver.last_solve_info = None
+    monkeypatch.setenv("NDCN_GENERIC_FUSED", "0")
+    b = nb.odeint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-8)
+    assert solver.last_solve_info is None
+    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
